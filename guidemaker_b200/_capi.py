@@ -1,0 +1,221 @@
+"""ctypes binding of libgm_b200.so (include/gm_b200.h).  Thin: numpy arrays in, numpy arrays out.
+
+There is deliberately no CPU fallback here: if the shared library is missing or no sm_100 device
+is present every call raises (``EngineUnavailable`` / ``RuntimeError``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from ._build import LIBPATH
+
+METRIC_HAMMING, METRIC_LEVEN = 0, 1
+MAX_L, MAX_K, MAX_PAM = 27, 32, 8
+
+_c_i64p = ctypes.POINTER(ctypes.c_int64)
+_vp = ctypes.c_void_p
+
+
+class EngineUnavailable(RuntimeError):
+    """libgm_b200.so could not be loaded or no B200-class device is usable."""
+
+
+_LIB = None
+
+_SIGS = {
+    "gm_init": [ctypes.c_int],
+    "gm_version": [],
+    "gm_device_info": [ctypes.POINTER(ctypes.c_int)] * 3 + [_c_i64p],
+    "gm_scan_create": [_vp, ctypes.c_int64, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                       ctypes.POINTER(_vp), _c_i64p, _c_i64p],
+    "gm_scan_fetch": [_vp, _vp, _vp, _vp],
+    "gm_scan_free": [_vp],
+    "gm_seed_dedup": [_vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp],
+    "gm_first_occurrence": [_vp, ctypes.c_int64, _vp],
+    "gm_index_create": [_vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)],
+    "gm_index_create_dev": [_vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp), _vp],
+    "gm_index_info": [_vp, _c_i64p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)],
+    "gm_index_free": [_vp],
+    "gm_knn": [_vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp],
+    "gm_knn_dev": [_vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp],
+    "gm_min_dist": [_vp, _vp, ctypes.c_int64, _vp],
+    "gm_min_dist_dev": [_vp, _vp, ctypes.c_int64, _vp, _vp],
+    "gm_prof_enable": [ctypes.c_int],
+    "gm_prof_reset": [],
+    "gm_prof_read": [ctypes.POINTER(ctypes.c_double), _c_i64p, ctypes.POINTER(ctypes.c_double), _c_i64p],
+    "gm_knn_tune": [ctypes.c_int, ctypes.c_int, ctypes.c_int],
+    "gm_microbench": [ctypes.c_int, ctypes.POINTER(ctypes.c_double)],
+}
+EXPORTS = tuple(_SIGS) + ("gm_last_error",)
+
+
+def load_library(path: str = LIBPATH) -> ctypes.CDLL:
+    """dlopen the engine and declare every prototype of include/gm_b200.h (no CUDA call is made)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(path):
+            raise EngineUnavailable(
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). guidemaker_b200 has no CPU fallback.")
+        try:
+            lib = ctypes.CDLL(path)
+        except OSError as e:  # e.g. libcudart not found
+            raise EngineUnavailable(f"cannot load {path}: {e}") from e
+        for name, args in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = ctypes.c_int
+        lib.gm_last_error.argtypes = []
+        lib.gm_last_error.restype = ctypes.c_char_p
+        _LIB = lib
+    return _LIB
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load_library().gm_last_error().decode(errors="replace")
+        if rc == -4:
+            raise EngineUnavailable(f"{what}: {msg}")
+        if rc == -2:
+            raise ValueError(f"{what}: {msg}")
+        if rc == -3:
+            raise MemoryError(f"{what}: {msg}")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+_initialised = False
+
+
+def init(device: int | None = None) -> None:
+    """Bind the CUDA device (default: LOCAL_RANK or 0).  Raises EngineUnavailable without a B200."""
+    global _initialised
+    if _initialised and device is None:
+        return
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    _check(load_library().gm_init(device), "gm_init")
+    _initialised = True
+
+
+def device_info() -> dict:
+    init()
+    sm, ma, mi, mem = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+    _check(load_library().gm_device_info(ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi), ctypes.byref(mem)), "gm_device_info")
+    return {"sm_count": sm.value, "cc": (ma.value, mi.value), "mem_bytes": mem.value}
+
+
+# ---- K1 ---------------------------------------------------------------------------------------------
+def pam_scan(seq: bytes | np.ndarray, pam: str, five_prime: bool, L: int):
+    """-> (guide2bit u64[n], start u32[n], pamcode u16[n], n_fwd, n_rev); forward rows first."""
+    init()
+    lib = load_library()
+    buf = np.frombuffer(seq, dtype=np.uint8) if not isinstance(seq, np.ndarray) else np.ascontiguousarray(seq, np.uint8)
+    h, nf, nr = _vp(), ctypes.c_int64(), ctypes.c_int64()
+    _check(lib.gm_scan_create(_p(buf) if len(buf) else None, len(buf), pam.encode("ascii", "replace"), len(pam), int(bool(five_prime)),
+                              int(L), ctypes.byref(h), ctypes.byref(nf), ctypes.byref(nr)), "gm_scan_create")
+    try:
+        n = nf.value + nr.value
+        g = np.empty(n, np.uint64); s = np.empty(n, np.uint32); p = np.empty(n, np.uint16)
+        if n:
+            _check(lib.gm_scan_fetch(h, _p(g), _p(s), _p(p)), "gm_scan_fetch")
+    finally:
+        lib.gm_scan_free(h)
+    return g, s, p, nf.value, nr.value
+
+
+# ---- K2 ---------------------------------------------------------------------------------------------
+def seed_dedup(guides: np.ndarray, L: int, lsr: int, five_prime: bool) -> np.ndarray:
+    init()
+    guides = np.ascontiguousarray(guides, np.uint64)
+    out = np.zeros(len(guides), np.uint8)
+    _check(load_library().gm_seed_dedup(_p(guides), len(guides), int(L), int(lsr), int(bool(five_prime)), _p(out)), "gm_seed_dedup")
+    return out.view(np.bool_)
+
+
+def first_occurrence(keys: np.ndarray) -> np.ndarray:
+    init()
+    keys = np.ascontiguousarray(keys, np.uint64)
+    out = np.zeros(len(keys), np.int64)
+    _check(load_library().gm_first_occurrence(_p(keys), len(keys), _p(out)), "gm_first_occurrence")
+    return out
+
+
+# ---- K3/K4/K5 ---------------------------------------------------------------------------------------
+class Index:
+    """Owns one gm index handle (the distinct-guide table resident in HBM)."""
+
+    def __init__(self, uniq2bit, L: int, metric: int, device_ptr: int | None = None, n: int | None = None, stream: int = 0):
+        init()
+        self._h = _vp()
+        self.L, self.metric = int(L), int(metric)
+        lib = load_library()
+        if device_ptr is None:
+            uniq2bit = np.ascontiguousarray(uniq2bit, np.uint64)
+            self.n = len(uniq2bit)
+            _check(lib.gm_index_create(_p(uniq2bit) if self.n else None, self.n, self.L, self.metric, ctypes.byref(self._h)), "gm_index_create")
+        else:
+            self.n = int(n)
+            _check(lib.gm_index_create_dev(_vp(device_ptr), self.n, self.L, self.metric, ctypes.byref(self._h), _vp(stream)), "gm_index_create_dev")
+
+    def knn(self, q2bit: np.ndarray, k: int):
+        q2bit = np.ascontiguousarray(q2bit, np.uint64)
+        q = len(q2bit)
+        idx = np.empty((q, k), np.int32); dist = np.empty((q, k), np.uint8)
+        _check(load_library().gm_knn(self._h, _p(q2bit) if q else None, q, int(k), _p(idx), _p(dist)), "gm_knn")
+        return idx, dist
+
+    def min_dist(self, q2bit: np.ndarray) -> np.ndarray:
+        q2bit = np.ascontiguousarray(q2bit, np.uint64)
+        dist = np.empty(len(q2bit), np.uint8)
+        _check(load_library().gm_min_dist(self._h, _p(q2bit) if len(q2bit) else None, len(q2bit), _p(dist)), "gm_min_dist")
+        return dist
+
+    def knn_dev(self, d_q: int, q: int, k: int, d_idx: int, d_dist: int, stream: int = 0) -> None:
+        _check(load_library().gm_knn_dev(self._h, _vp(d_q), int(q), int(k), _vp(d_idx), _vp(d_dist), _vp(stream)), "gm_knn_dev")
+
+    def min_dist_dev(self, d_q: int, q: int, d_dist: int, stream: int = 0) -> None:
+        _check(load_library().gm_min_dist_dev(self._h, _vp(d_q), int(q), _vp(d_dist), _vp(stream)), "gm_min_dist_dev")
+
+    def close(self):
+        if self._h:
+            load_library().gm_index_free(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- measurement hooks ------------------------------------------------------------------------------
+def prof_enable(on: bool = True):
+    _check(load_library().gm_prof_enable(int(on)), "gm_prof_enable")
+
+
+def prof_reset():
+    _check(load_library().gm_prof_reset(), "gm_prof_reset")
+
+
+def prof_read() -> dict:
+    ms, n, pairs, alln = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double(), ctypes.c_int64()
+    _check(load_library().gm_prof_read(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(pairs), ctypes.byref(alln)), "gm_prof_read")
+    return {"scan_kernel_ms": ms.value, "scan_kernel_launches": n.value, "pairs": pairs.value, "all_kernel_launches": alln.value}
+
+
+def knn_tune(queries_per_thread: int = 0, splits: int = 0, warm_sample: int = -1):
+    _check(load_library().gm_knn_tune(queries_per_thread, splits, warm_sample), "gm_knn_tune")
+
+
+def microbench(what: int) -> float:
+    init()
+    v = ctypes.c_double()
+    _check(load_library().gm_microbench(int(what), ctypes.byref(v)), "gm_microbench")
+    return v.value

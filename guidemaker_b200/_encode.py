@@ -1,0 +1,76 @@
+"""Vectorised host-side conversion between guide strings and the packed ``guide2bit`` format
+(base i in bits [2i,2i+1], A=0 C=1 G=2 T=3).  No per-row Python."""
+from __future__ import annotations
+
+import numpy as np
+
+_ASCII = np.frombuffer(b"ACGT", dtype=np.uint8)
+_LUT = np.full(256, 255, dtype=np.uint8)
+_LUT[_ASCII] = np.arange(4, dtype=np.uint8)
+
+
+def as_byte_matrix(seqs, L: int | None = None) -> np.ndarray:
+    """list/array/Series of equal-length ASCII strings -> (N, L) uint8 matrix."""
+    if isinstance(seqs, np.ndarray) and seqs.dtype == np.uint8 and seqs.ndim == 2:
+        return seqs
+    try:
+        import pandas as pd
+        if isinstance(seqs, (pd.Series, pd.Index)):
+            seqs = seqs.to_numpy(dtype=object, na_value="")
+    except ImportError:  # pragma: no cover
+        pass
+    arr = np.asarray(seqs)
+    if arr.dtype.kind != "S":
+        arr = np.asarray(arr, dtype=object)
+        lens = np.fromiter((len(s) for s in arr), dtype=np.int64, count=len(arr))
+        width = int(L if L is not None else (lens.max() if len(lens) else 0))
+        if len(arr) and (lens != width).any():
+            raise ValueError("all guide sequences must have the same length (%d)" % width)
+        arr = arr.astype("S%d" % max(width, 1)) if len(arr) else np.empty(0, dtype="S%d" % max(width, 1))
+    width = arr.dtype.itemsize
+    if L is not None and len(arr) and width != L:
+        raise ValueError("all guide sequences must have the same length (%d)" % L)
+    return np.ascontiguousarray(arr).view(np.uint8).reshape(len(arr), width)
+
+
+def encode_matrix(mat: np.ndarray) -> np.ndarray:
+    """(N, L) uint8 ASCII -> uint64 guide2bit.  Raises on anything but upper-case A/C/G/T."""
+    n, L = mat.shape
+    if L > 27:
+        raise ValueError("guides longer than 27 nt are not supported (got %d)" % L)
+    codes = _LUT[mat]
+    if n and codes.max(initial=0) > 3:
+        raise ValueError("guide sequences may contain only A, C, G, T")
+    out = np.zeros(n, dtype=np.uint64)
+    for i in range(L):
+        out |= codes[:, i].astype(np.uint64) << np.uint64(2 * i)
+    return out
+
+
+def encode_guides(seqs, L: int | None = None) -> np.ndarray:
+    return encode_matrix(as_byte_matrix(seqs, L))
+
+
+def decode_matrix(g: np.ndarray, L: int) -> np.ndarray:
+    """uint64 guide2bit -> (N, L) uint8 ASCII matrix."""
+    g = np.asarray(g, dtype=np.uint64)
+    out = np.empty((len(g), L), dtype=np.uint8)
+    for i in range(L):
+        out[:, i] = _ASCII[((g >> np.uint64(2 * i)) & np.uint64(3)).astype(np.intp)]
+    return out
+
+
+def decode_guides(g: np.ndarray, L: int) -> np.ndarray:
+    """uint64 guide2bit -> numpy array of dtype S{L}."""
+    if L == 0:
+        return np.zeros(len(g), dtype="S1")
+    return decode_matrix(g, L).view("S%d" % L).reshape(len(g))
+
+
+def matrix_to_strings(mat: np.ndarray):
+    """(N, W) uint8 -> pandas-ready string array without creating Python objects (Arrow buffers)."""
+    import pyarrow as pa
+    n, w = mat.shape
+    offsets = pa.py_buffer((np.arange(n + 1, dtype=np.int64) * w))
+    data = pa.py_buffer(np.ascontiguousarray(mat))
+    return pa.LargeStringArray.from_buffers(n, offsets, data)

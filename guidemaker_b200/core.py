@@ -1,0 +1,394 @@
+"""Hot-path surface of ``guidemaker.core`` on the B200 engine.
+
+Same class names, constructor/method signatures, attribute names, DataFrame schema and error
+behaviour as /root/reference/guidemaker/core.py for the off-target path:
+
+    PamTarget.__init__ / find_targets                          core.py:49-69, :83-292
+    TargetProcessor.__init__ / check_restriction_enzymes /
+        find_unique_near_pam / create_index / get_neighbors /
+        export_bed / get_control_seqs                          core.py:304-633
+    extend_ambiguous_dna                                       core.py:1093-1124
+
+All arithmetic (PAM scan, seed duplicate flags, distinct-guide table, exact kNN, control
+min-distance) runs in ``libgm_b200.so``; this module only moves arrays in and out of pandas
+without per-row Python.  There is no CPU fallback: without the CUDA engine every hot method raises.
+
+Deliberate, documented differences from the reference:
+  Q2/Q3  the index holds the distinct guides in FIRST-OCCURRENCE order (the reference uses the
+         process-random order of ``list(set(...))``) and ``neighbors[seq]["neighbors"]["seqs"]``
+         are the true neighbour sequences (the reference maps ids through the wrong table);
+  Q14    the search is exact, so distances can only be <= the reference's approximate HNSW ones;
+  ``self.neighbors`` is a read-only Mapping backed by arrays, not a dict of dicts;
+  ``exact_pam`` / ``seqid`` are always categorical (the reference's concat silently degrades them to
+         strings when per-record categories differ).
+"""
+from __future__ import annotations
+
+import hashlib
+import logging
+import statistics
+from copy import deepcopy
+from itertools import product
+from typing import List
+
+import numpy as np
+import pandas as pd
+import yaml
+
+from . import _capi
+from ._encode import as_byte_matrix, decode_matrix, encode_matrix, matrix_to_strings
+from .neighbors import ExactIndex, NeighborMap
+from .sharding import sharded_knn, sharded_min_dist
+
+logger = logging.getLogger(__name__)
+
+_IUPAC_LETTERS = ['A', 'C', 'G', 'T', 'M', 'R', 'W', 'S', 'Y', 'K', 'V', 'H', 'D', 'B', 'X', 'N']
+
+# Bio.Seq.reverse_complement as used at core.py:95-106: IUPAC aware, other bytes unchanged
+_COMP_FROM = b"ACGTMRWSYKVHDBXNacgtmrwsykvhdbxn"
+_COMP_TO = b"TGCAKYWSRMBDHVXNtgcakywsrmbdhvxn"
+_COMP_LUT = np.arange(256, dtype=np.uint8)
+_COMP_LUT[np.frombuffer(_COMP_FROM, np.uint8)] = np.frombuffer(_COMP_TO, np.uint8)
+_COMP_TABLE = bytes.maketrans(_COMP_FROM, _COMP_TO)
+
+
+def _reverse_complement(s: str) -> str:
+    return s.translate(str.maketrans(_COMP_FROM.decode(), _COMP_TO.decode()))[::-1]
+
+
+def _str_series(mat: np.ndarray, index=None) -> pd.Series:
+    """(N, W) ASCII matrix -> pandas str Series built from Arrow buffers (no Python objects)."""
+    if mat.shape[1] == 0:
+        return pd.Series([""] * len(mat), dtype="str", index=index)
+    return pd.Series(pd.array(matrix_to_strings(mat), dtype="str"), index=index)
+
+
+def _series_matrix(s: pd.Series) -> np.ndarray:
+    """str Series of equal-length guides -> (N, L) uint8, zero-copy from Arrow when possible."""
+    try:
+        import pyarrow as pa
+        arr = pa.array(s, type=pa.large_string()) if not hasattr(s.array, "_pa_array") else s.array._pa_array
+        if isinstance(arr, pa.ChunkedArray):
+            arr = arr.combine_chunks()
+        if arr.null_count == 0 and len(arr):
+            if pa.types.is_string(arr.type):
+                arr = arr.cast(pa.large_string())
+            bufs = arr.buffers()
+            off = np.frombuffer(bufs[1], dtype=np.int64)[arr.offset: arr.offset + len(arr) + 1]
+            width = int(off[1] - off[0])
+            if width > 0 and np.array_equal(off, off[0] + np.arange(len(arr) + 1, dtype=np.int64) * width):
+                data = np.frombuffer(bufs[2], dtype=np.uint8)[off[0]: off[-1]]
+                return data.reshape(len(arr), width)
+    except Exception:  # noqa: BLE001 -- any surprise falls back to the generic (slower) route
+        pass
+    return as_byte_matrix(s)
+
+
+class PamTarget:
+    """A Protospacer Adjacent Motif (PAM) and its targets (core.py:39-292)."""
+
+    def __init__(self, pam: str, pam_orientation: str, dtype: str) -> None:
+        for letter in pam.upper():
+            assert letter in _IUPAC_LETTERS
+        assert pam_orientation in ["3prime", "5prime"]
+        self.pam: str = pam.upper()
+        self.pam_orientation: str = pam_orientation
+        self.dtype: str = dtype
+
+    def __str__(self) -> str:
+        return "A PAM object: {self.pam}".format(self=self)
+
+    def find_targets(self, seq_record_iter: object, target_len: int) -> pd.DataFrame:
+        """All targets next to a PAM match on both strands (core.py:83-292).
+
+        Records are duck-typed: ``.id`` and ``str(.seq)``.  Row order, coordinates and the 12-column
+        schema are the reference's: per record all forward hits (ascending), then all reverse hits.
+        """
+        five = self.pam_orientation == "5prime"
+        P, L = len(self.pam), int(target_len)
+        ids, seqs, raw = [], [], []
+        for record in seq_record_iter:
+            ids.append(record.id)
+            s = str(record.seq)
+            seqs.append(s)
+            raw.append(s.encode("latin-1", "replace"))
+        # one launch over the whole genome: records joined by an invalid base, which can neither
+        # match a PAM position nor sit inside a target, so no hit straddles two records
+        lens = np.array([len(b) for b in raw], dtype=np.int64)
+        rec_start = np.zeros(len(raw) + 1, dtype=np.int64)
+        if len(raw):
+            rec_start[1:] = np.cumsum(lens + 1)
+        buf = b"N".join(raw)
+        if len(buf) == 0 and not raw:
+            return pd.concat([])                     # the reference raises ValueError on no records
+        guides, gstart, pamcode, n_fwd, n_rev = _capi.pam_scan(buf, self.pam, five, L)
+        n = n_fwd + n_rev
+        if n == 0:
+            return pd.concat([])                     # zero hits -> ValueError (core.py:286-287)
+        strand = np.zeros(n, dtype=bool)
+        strand[:n_fwd] = True
+        rec = np.searchsorted(rec_start, gstart.astype(np.int64), side="right") - 1
+        if len(raw) > 1:                             # stable by record: forward block stays ahead of reverse block
+            order = np.argsort(rec, kind="stable")
+            guides, gstart, pamcode, strand, rec = guides[order], gstart[order], pamcode[order], strand[order], rec[order]
+        start = (gstart.astype(np.int64) - rec_start[rec])
+
+        seq30 = self._target_seq30(np.frombuffer(buf, np.uint8), seqs, rec, rec_start, lens, start, strand, five, P, L)
+        df = pd.DataFrame({
+            "target": _str_series(decode_matrix(guides, L)),
+            "exact_pam": pd.Categorical(_str_series(decode_matrix(pamcode.astype(np.uint64), P))),
+            "start": start.astype(np.uint32),
+            "stop": (start + L).astype(np.uint32),
+            "strand": strand,
+            "pam_orientation": np.full(n, five, dtype=bool),
+            "target_seq30": seq30,
+            "seqid": pd.Categorical.from_codes(rec, categories=pd.Index(ids).unique()) if len(set(ids)) == len(ids)
+            else pd.Categorical(np.asarray(ids, dtype=object)[rec]),
+        })
+        df = df.assign(seedseq=np.nan, hasrestrictionsite=np.nan, isseedduplicated=np.nan)
+        df = df.astype({"seedseq": 'str', "isseedduplicated": 'bool'})
+        df = df.assign(dtype=self.dtype)
+        df = df.astype({"dtype": 'category'})
+        return df
+
+    @staticmethod
+    def _target_seq30(buf, seqs, rec, rec_start, lens, start, strand, five, P, L) -> pd.Series:
+        """The 30-nt context column (core.py:156,184,210-211,237): a Python slice of the record
+        around the match, reverse-complemented for reverse hits, NOT validated."""
+        n = len(start)
+        # match start/end on the forward text, from the target window
+        if five:
+            ms = np.where(strand, start - P, start + L)
+        else:
+            ms = np.where(strand, start + L, start - P)
+        me = ms + P
+        use_ms = strand == five                       # 5p fwd / 3p rev slice [ms-3, ms+27); others [me-27, me+3)
+        a = np.where(use_ms, ms - 3, me - 27)
+        interior = (a >= 0) & (a + 30 <= lens[rec])
+        out = np.empty((n, 30), dtype=np.uint8)
+        if len(buf) >= 30 and interior.any():
+            win = np.lib.stride_tricks.sliding_window_view(buf, 30)
+            out[interior] = win[(a + rec_start[rec])[interior]]
+        rev = interior & ~strand
+        if rev.any():
+            out[rev] = _COMP_LUT[out[rev][:, ::-1]]
+        if interior.all():
+            return _str_series(out)
+        out[~interior] = ord("?")
+        col = _str_series(out).astype(object)
+        for i in np.flatnonzero(~interior):           # near record ends: literal Python slicing, as the reference
+            s = seqs[rec[i]]
+            piece = s[int(a[i]): int(a[i]) + 30]
+            col.iat[i] = piece if strand[i] else _reverse_complement(piece)
+        return col.astype("str")
+
+
+class TargetProcessor:
+    """A set of guide RNA targets (core.py:295-633)."""
+
+    def __init__(self, targets: pd.DataFrame, lsr: int, editdist: int = 2, knum: int = 2) -> None:
+        self.targets = targets
+        self.lsr: int = lsr
+        self.editdist: int = editdist
+        self.knum: int = knum
+        self.nmslib_index: object = None
+        self.neighbors: dict = {}
+        self.closest_neighbor_df: pd.DataFrame = None
+        self.ncontrolsearched: int = None
+        self.gc_percent: float = None
+        self.genomesize: float = None
+        self.pam_orientation: bool = targets['pam_orientation'].iat[0]
+
+    def __str__(self) -> None:
+        info = "TargetList: contains a set of {} potential PAM targets".format(len(self.targets))
+        return info
+
+    def __len__(self) -> int:
+        return len(self.targets)
+
+    # ---- helpers -------------------------------------------------------------------------------------
+    def _is_hamming(self) -> bool:
+        return self.targets['dtype'].iat[0] == "hamming"       # anything else means Levenshtein (core.py:448,458)
+
+    def _guide_matrix(self) -> np.ndarray:
+        mat = _series_matrix(self.targets['target'])
+        if mat.shape[1] > _capi.MAX_L:
+            raise ValueError("guides longer than %d nt are not supported" % _capi.MAX_L)
+        return mat
+
+    def _packed(self):
+        mat = self._guide_matrix()
+        return encode_matrix(mat), mat.shape[1]
+
+    # ---- reference API -------------------------------------------------------------------------------
+    def check_restriction_enzymes(self, restriction_enzyme_list: list = []) -> None:
+        """Flag guides containing a restriction site or its reverse complement (core.py:354-377)."""
+        element_to_exclude = []
+        for record in set(restriction_enzyme_list):
+            for letter in record.upper():
+                assert letter in _IUPAC_LETTERS
+            element_to_exclude.append(extend_ambiguous_dna(record.upper()))
+            element_to_exclude.append(extend_ambiguous_dna(_reverse_complement(record.upper())))
+        element_to_exclude = sum(element_to_exclude, [])
+        if len(element_to_exclude) > 0:
+            self.targets['hasrestrictionsite'] = self.targets['target'].str.contains('|'.join(element_to_exclude))
+        else:
+            self.targets['hasrestrictionsite'] = False
+
+    def _one_hot_encode(self, seq_list: List[object]) -> List[str]:
+        """nmslib bit_hamming text format (core.py:379-386); kept for callers of the facade."""
+        charmap = {'A': '1 0 0 0', 'C': '0 1 0 0', 'G': '0 0 1 0', 'T': '0 0 0 1'}
+        return [" ".join(charmap[letter] for letter in seq) for seq in seq_list]
+
+    def find_unique_near_pam(self) -> None:
+        """seedseq = PAM-proximal ``lsr`` nt; isseedduplicated = keep-first duplicate flag (core.py:388-416)."""
+        self.targets = deepcopy(self.targets)
+        mat = self._guide_matrix()
+        L = mat.shape[1]
+        five = bool(self.pam_orientation)
+        lsr = int(self.lsr)
+        if lsr == 0 or (five and lsr >= L):
+            seed, lsr_eff = mat, 0
+        elif five:
+            seed, lsr_eff = mat[:, 0:lsr], lsr
+        else:
+            cut = L - lsr                              # tseq[(len(tseq) - lsr):], Python slice semantics
+            if cut < 0:
+                cut = max(L + cut, 0)
+            seed, lsr_eff = mat[:, cut:], L - cut
+        self.targets['seedseq'] = _str_series(np.ascontiguousarray(seed), index=self.targets.index)
+        self.targets['isseedduplicated'] = _capi.seed_dedup(encode_matrix(mat), L, lsr_eff if lsr_eff < L else 0, five)
+
+    def create_index(self, configpath: str, num_threads=2):
+        """Upload the distinct guides to the GPU (replaces the HNSW build, core.py:418-467).
+
+        ``NMSLIB.{M,efc,post}`` are read (a missing key raises as in the reference) and ignored: the
+        search is exact.  ``num_threads`` is accepted and ignored."""
+        with open(configpath) as cf:
+            config = yaml.safe_load(cf)
+        M, efC, post = config['NMSLIB']['M'], config['NMSLIB']['efc'], config['NMSLIB']['post']  # noqa: F841
+        guides, L = self._packed()
+        first_row = _capi.first_occurrence(guides)
+        is_first = first_row == np.arange(len(guides))
+        uniq = np.ascontiguousarray(guides[is_first])
+        metric = _capi.METRIC_HAMMING if self._is_hamming() else _capi.METRIC_LEVEN
+        self.nmslib_index = ExactIndex(uniq, L, metric)
+
+    def get_neighbors(self, configpath, num_threads=2) -> None:
+        """k nearest guides of every query row; keep a query iff its nearest OTHER guide is at least
+        ``editdist`` away (core.py:471-523).  Writes ``self.neighbors``."""
+        with open(configpath) as cf:
+            config = yaml.safe_load(cf)
+        ef = config['NMSLIB']['ef']  # noqa: F841  (HNSW efSearch; no-op for the exact search)
+        t = self.targets
+        qmask = ((t['isseedduplicated'] == False) | (t['hasrestrictionsite'] == False)).to_numpy(dtype=bool)  # noqa: E712
+        guides, L = self._packed()
+        q = np.ascontiguousarray(guides[qmask])
+        index = self.nmslib_index
+        index.setQueryTimeParams({'efSearch': ef})
+        if len(q) == 0:
+            self.neighbors = NeighborMap(q, np.zeros((0, self.knum), np.int32), np.zeros((0, self.knum), np.uint8), index.uniq, L)
+            return
+        idx, dist = sharded_knn(index, q, int(self.knum))
+        if dist.shape[1] < 2 or (idx[:, 1] < 0).any():
+            raise IndexError("list index out of range")    # editdist[1] with fewer than 2 hits (core.py:512,518)
+        keep = dist[:, 1] >= int(self.editdist)
+        self.neighbors = NeighborMap(q[keep], idx[keep], dist[keep], index.uniq, L)
+
+    def export_bed(self) -> object:
+        """Rows with a first-seen seed as a BED-like frame sorted by (chrom, start) (core.py:525-543)."""
+        df = deepcopy(self.targets.loc[self.targets['isseedduplicated'] == False])  # noqa: E712
+        df = df[["seqid", "start", "stop", "target", "strand"]]
+        df = df.assign(strand=np.where(df['strand'].to_numpy(dtype=bool), '+', '-'))
+        df.columns = ["chrom", "chromstart", "chromend", "name", "strand"]
+        df = df.sort_values(by=['chrom', 'chromstart'])
+        return df
+
+    def get_control_seqs(self, seq_record_iter: object, configpath, length: int = 20, n: int = 10,
+                         num_threads: int = 2) -> pd.DataFrame:
+        """Random GC-matched sequences farthest from every indexed guide (core.py:545-633).
+
+        Draws from numpy's global legacy RNG in the reference's stream order (one uniform per base,
+        letters ["G","C","A","T"]), so a caller that seeds ``np.random.seed`` gets the sequences the
+        reference would draw."""
+        with open(configpath) as cf:
+            config = yaml.safe_load(cf)
+        MINIMUM_HMDIST = config['CONTROL']['MINIMUM_HMDIST']
+        MAX_CONTROL_SEARCH_MULTIPLE = max(config['CONTROL']['CONTROL_SEARCH_MULTIPLE'])
+        CONTROL_SEARCH_MULTIPLE = config['CONTROL']['CONTROL_SEARCH_MULTIPLE']
+
+        totlen = 0
+        gccnt = 0
+        for record in seq_record_iter:
+            gccnt += _gc_fraction(str(record.seq)) * len(record)
+            totlen += len(record)
+        gc = gccnt / (totlen)
+        self.gc_percent = gc * 100
+        self.genomesize = totlen / (1024 * 1024)
+
+        hamming = self._is_hamming()
+        index = self.nmslib_index
+        if int(length) != index.L:
+            raise ValueError("control length %d does not match the index (guide length %d)" % (length, index.L))
+        cdf = np.cumsum(np.array([gc / 2, gc / 2, (1 - gc) / 2, (1 - gc) / 2], dtype=np.float64))
+        cdf /= cdf[-1]
+        letter_code = np.array([2, 1, 0, 3], dtype=np.uint64)       # "G","C","A","T" -> guide2bit codes
+        shifts = (2 * np.arange(length, dtype=np.uint64))[None, :]
+
+        minimum_hmdist = 0
+        sm_count = 0
+        search_mult = 0
+        try:
+            while minimum_hmdist < MINIMUM_HMDIST or search_mult == MAX_CONTROL_SEARCH_MULTIPLE:
+                search_mult = CONTROL_SEARCH_MULTIPLE[sm_count]
+                total = n * search_mult
+                codes = np.empty(total, dtype=np.uint64)
+                dist = np.empty(total, dtype=np.uint8)
+                step = 1 << 20
+                for lo in range(0, total, step):                   # bounded host memory; same RNG stream order
+                    hi = min(lo + step, total)
+                    u = np.random.random_sample((hi - lo, length))
+                    sel = letter_code[np.searchsorted(cdf, u, side="right")]
+                    codes[lo:hi] = np.bitwise_or.reduce(sel << shifts, axis=1)
+                    dist[lo:hi] = sharded_min_dist(index, codes[lo:hi])
+                order = np.argsort(-dist.astype(np.int64), kind="stable")[:n]   # descending, ties in draw order
+                sort_codes = codes[order]
+                if hamming:
+                    sort_dist = [float(x) for x in dist[order]]     # nmslib bit distance / 2 (core.py:613)
+                else:
+                    sort_dist = [int(x) for x in dist[order]]
+                minimum_hmdist = int(min(sort_dist))
+                sm_count += 1
+        except IndexError as e:
+            raise e
+
+        total_ncontrolsearched = search_mult * n
+        self.ncontrolsearched = total_ncontrolsearched
+        sort_seq = [s.decode() for s in decode_matrix(sort_codes, length).view("S%d" % length).reshape(-1)]
+        randomdf = pd.DataFrame(data={"Sequences": sort_seq, "Hamming distance": sort_dist})
+
+        def create_name(seq):
+            return "Cont-" + hashlib.md5(seq.encode()).hexdigest()
+        randomdf['name'] = randomdf["Sequences"].apply(create_name)
+        randomdf = randomdf[["name", "Sequences", "Hamming distance"]]
+        return (min(sort_dist),
+                statistics.median(sort_dist),
+                randomdf)
+
+
+def _gc_fraction(seq: str) -> float:
+    """Bio.SeqUtils.gc_fraction(seq) with its default ambiguous="remove" (core.py:575):
+    (G+C+S) / (G+C+S+A+T+W+U), case-insensitive, 0 for an empty denominator."""
+    counts = np.bincount(np.frombuffer(seq.encode("latin-1", "replace"), np.uint8), minlength=256)
+    gc = int(sum(counts[ord(c)] for c in "CGScgs"))
+    at = int(sum(counts[ord(c)] for c in "ATWUatwu"))
+    return gc / (gc + at) if gc + at else 0
+
+
+def extend_ambiguous_dna(seq: str) -> List[str]:
+    """All concrete sequences of an IUPAC string, in the reference's order (core.py:1093-1124)."""
+    ambiguous_dna_values = {
+        "A": "A", "C": "C", "G": "G", "T": "T", "M": "AC", "R": "AG", "W": "AT", "S": "CG", "Y": "CT",
+        "K": "GT", "V": "ACG", "H": "ACT", "D": "AGT", "B": "CGT", "X": "GATC", "N": "GATC",
+    }
+    return ["".join(i) for i in product(*[ambiguous_dna_values[j] for j in seq])]

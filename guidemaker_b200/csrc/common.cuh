@@ -1,0 +1,110 @@
+// common.cuh -- shared host/device helpers of libgm_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/gm_b200.h"
+
+namespace gm {
+
+// ---- error plumbing (thread-local message behind gm_last_error) -----------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define GM_CUDA(call)                                                        \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) return gm::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define GM_ARG(cond, ...)                                                    \
+    do {                                                                     \
+        if (!(cond)) { gm::set_error(__VA_ARGS__); return GM_ERR_ARG; }      \
+    } while (0)
+
+// ---- profiling counters (gm_prof_*) ----------------------------------------------------------------
+struct Prof {
+    bool on = false;
+    long long all_launches = 0;
+    long long scan_launches = 0;
+    double pairs = 0.0;
+    double scan_ms_done = 0.0;       // already synchronised and summed
+    static const int MAXEV = 4096;
+    cudaEvent_t ev[MAXEV][2];
+    int n_ev = 0, n_alloc = 0;
+};
+Prof &prof();
+inline void count_launch(int n = 1) { prof().all_launches += n; }
+
+int device_sm_count();
+bool initialised();
+int ensure_init();
+
+// ---- device helpers ---------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// mbarrier + 1-D bulk async copy (TMA engine, SASS: UBLKCP) -- used to stream the target table
+// through shared memory.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy, completion signalled on `bar` as transaction bytes.
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 2-bit interleaved guide -> bit planes: lo bit i = bit 2i, hi bit i = bit 2i+1.
+__device__ __forceinline__ uint32_t compress_even_bits(uint64_t x) {
+    x &= 0x5555555555555555ULL;
+    x = (x | (x >> 1)) & 0x3333333333333333ULL;
+    x = (x | (x >> 2)) & 0x0F0F0F0F0F0F0F0FULL;
+    x = (x | (x >> 4)) & 0x00FF00FF00FF00FFULL;
+    x = (x | (x >> 8)) & 0x0000FFFF0000FFFFULL;
+    x = (x | (x >> 16)) & 0x00000000FFFFFFFFULL;
+    return static_cast<uint32_t>(x);
+}
+__device__ __forceinline__ uint2 to_planes(uint64_t g) {
+    return make_uint2(compress_even_bits(g), compress_even_bits(g >> 1));
+}
+__device__ __forceinline__ uint64_t spread_bits(uint32_t v) {
+    uint64_t x = v;
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFFULL;
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FFULL;
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0FULL;
+    x = (x | (x << 2)) & 0x3333333333333333ULL;
+    x = (x | (x << 1)) & 0x5555555555555555ULL;
+    return x;
+}
+__device__ __forceinline__ uint64_t from_planes(uint32_t lo, uint32_t hi) {
+    return spread_bits(lo) | (spread_bits(hi) << 1);
+}
+
+#endif  // __CUDACC__
+}  // namespace gm

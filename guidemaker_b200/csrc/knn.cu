@@ -1,0 +1,543 @@
+// knn.cu -- exact brute-force k-nearest-neighbour search over guides (K3a Hamming, K4 Levenshtein,
+// K5 min-distance) for sm_100a.  Replaces nmslib's HNSW index (core.py:418-523, :603-606).
+//
+// Layout in HBM
+//   index  : uint2 planes[n_pad]    (lo, hi) bit planes of every distinct guide, zero padded to a
+//            multiple of CHUNK so every bulk copy is full-sized.
+//   queries: uint2 qplanes[q_pad]   same layout, padded to a multiple of the query tile.
+//   lists  : uint32 keys[split][q_pad][k]  per (split, query) ascending list of
+//            key = (distance << 27) | target index, 0xFFFFFFFF = empty.
+//
+// Pair-scan kernel (the dominant kernel, one launch per gm_knn call plus an optional warm-up launch)
+//   grid = (query tiles, target splits).  A CTA owns THREADS*R queries -- R per thread, held in
+//   registers as planes -- and streams its split of the target table through shared memory in
+//   CHUNK-sized stages filled by the TMA engine (cp.async.bulk, completion on an mbarrier).  Every
+//   lane reads the same target (shared-memory broadcast) and evaluates it against its R queries:
+//   2 LOP3 + 1 POPC per pair.  Four distances are packed into the bytes of one word with
+//   multiply-adds on the FMA pipe and tested against the query's current k-th-best distance with a
+//   single biased subtraction: bit 7 of byte j is set iff distance j beats the threshold.  Only then
+//   (rare: the threshold tightens after a few hundred targets) does the thread fall into the
+//   insertion path, which keeps its private sorted list in global memory.  Targets stream in
+//   ascending index and an equal distance never displaces an earlier entry, which yields the
+//   deterministic (distance, index) order.
+//
+//   Warm start: an optional first launch scans only the first `warm` targets; its k-th-best
+//   distance per query is a valid upper bound and seeds the thresholds of the full scan, so the
+//   flood of insertions at the start of every split disappears.
+//
+// Merge kernel: k smallest keys over the splits of a query -> (int32 idx, uint8 dist) rows.
+#include "common.cuh"
+#include "distance.cuh"
+#include <new>
+
+namespace gm {
+
+int prof_begin(cudaStream_t s);
+void prof_end(int slot, cudaStream_t s, double pairs);
+
+static constexpr int CHUNK = 1024;      // targets per shared-memory stage (8 KB)
+static constexpr int NSTAGE = 3;
+static constexpr int THREADS = 128;
+static constexpr int MAX_SPLITS = 64;
+static constexpr uint32_t KEY_EMPTY = 0xFFFFFFFFu;
+static constexpr int IDX_BITS = 27;
+
+struct Index {
+    uint2 *planes = nullptr;
+    int64_t n_u = 0, n_pad = 0;
+    int L = 0, metric = 0;
+    void *ws = nullptr;
+    size_t ws_bytes = 0;
+};
+
+static int g_tune_r = 8;
+static int g_tune_splits = 0;
+static int g_tune_warm = -1;
+
+// ---- small kernels -------------------------------------------------------------------------------
+
+__global__ void to_planes_kernel(const uint64_t *__restrict__ g, int64_t n, int64_t n_pad, uint2 *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    out[i] = i < n ? to_planes(g[i]) : make_uint2(0u, 0u);
+}
+
+// ---- list maintenance ------------------------------------------------------------------------------
+
+// Insert key into the thread-private ascending list if it beats the current worst entry.
+// Returns the distance of the (new) worst entry, 31 while the list is not full.
+__device__ __noinline__ uint32_t list_insert(uint32_t *__restrict__ lst, int k, uint32_t key) {
+    uint32_t worst = lst[k - 1];
+    if (key < worst) {
+        int pos = k - 1;
+        while (pos > 0) {
+            uint32_t v = lst[pos - 1];
+            if (v <= key) break;
+            lst[pos] = v;
+            pos--;
+        }
+        lst[pos] = key;
+        worst = lst[k - 1];
+    }
+    return worst >> IDX_BITS;
+}
+
+// bias constant of the packed threshold test: byte = 128 + (tau - 1); after subtracting a distance
+// p <= 27 the byte keeps bit 7 iff p <= tau - 1, i.e. p < tau.  Bytes stay within [100, 158]: no
+// borrow ever crosses a byte boundary.
+__device__ __forceinline__ uint32_t bias_of(uint32_t tau) { return 0x7F7F7F7Fu + tau * 0x01010101u; }
+
+struct ScanArgs {
+    const uint2 *tplanes;
+    int n_chunks;             // chunks to cover (ceil(n_scan / CHUNK))
+    int chunks_per_split;
+    int64_t n_u;              // targets beyond this index are padding
+    const uint2 *qplanes;
+    int64_t q, q_pad;
+    int k;
+    uint32_t *lists;          // [gridDim.y][q_pad][k]
+    const uint32_t *warm;     // [q_pad][k] lists of the warm-up launch or nullptr
+    int L;
+};
+
+__device__ __forceinline__ void issue_chunk(uint2 *dst, const uint2 *src, uint64_t *bar) {
+    mbar_expect_tx(bar, CHUNK * (uint32_t)sizeof(uint2));
+    bulk_g2s(dst, src, CHUNK * (uint32_t)sizeof(uint2), bar);
+}
+
+// ---- K3a: Hamming pair scan --------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(THREADS) knn_hamming_scan_kernel(const ScanArgs a) {
+    __shared__ __align__(128) uint2 s_t[NSTAGE][CHUNK];
+    __shared__ __align__(8) uint64_t s_full[NSTAGE];
+
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.y * a.chunks_per_split;
+    const int c1 = min(c0 + a.chunks_per_split, a.n_chunks);
+    if (c0 >= c1) return;
+
+    const int64_t qbase = (int64_t)blockIdx.x * (THREADS * R) + tid;
+    uint32_t qlo[R], qhi[R], tau[R], C[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int64_t qi = qbase + (int64_t)r * THREADS;      // < q_pad by construction
+        const uint2 p = a.qplanes[qi];
+        qlo[r] = p.x;
+        qhi[r] = p.y;
+        uint32_t t = 31u;
+        if (a.warm) t = min((a.warm[(size_t)qi * a.k + (a.k - 1)] >> IDX_BITS) + 1u, 31u);
+        tau[r] = qi < a.q ? t : 0u;                           // padding queries never insert
+        C[r] = bias_of(tau[r]);
+    }
+    uint32_t *const my_lists = a.lists + ((size_t)blockIdx.y * a.q_pad + qbase) * a.k;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; s++) mbar_init(&s_full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE && c0 + s < c1; s++)
+            issue_chunk(s_t[s], a.tplanes + (size_t)(c0 + s) * CHUNK, &s_full[s]);
+    }
+
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int c = c0; c < c1; c++) {
+        mbar_wait(&s_full[stage], parity);
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(s_t[stage]);
+        const uint32_t tbase = (uint32_t)c * CHUNK;
+
+#pragma unroll 2
+        for (int g = 0; g < CHUNK / 4; g++) {
+            const uint4 t01 = s4[2 * g];          // targets 4g, 4g+1: (lo, hi, lo, hi) -- broadcast reads
+            const uint4 t23 = s4[2 * g + 1];      // targets 4g+2, 4g+3
+            uint32_t x[R];
+            uint32_t any = 0;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const uint32_t p0 = __popc((qlo[r] ^ t01.x) | (qhi[r] ^ t01.y));
+                const uint32_t p1 = __popc((qlo[r] ^ t01.z) | (qhi[r] ^ t01.w));
+                const uint32_t p2 = __popc((qlo[r] ^ t23.x) | (qhi[r] ^ t23.y));
+                const uint32_t p3 = __popc((qlo[r] ^ t23.z) | (qhi[r] ^ t23.w));
+                // pack on the FMA pipe: x = C - p0 - p1<<8 - p2<<16 - p3<<24
+                uint32_t v = C[r] - p0;
+                v = p1 * 0xFFFFFF00u + v;
+                v = p2 * 0xFFFF0000u + v;
+                v = p3 * 0xFF000000u + v;
+                x[r] = v;
+                any |= v;
+            }
+            if (any & 0x80808080u) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const uint32_t h = x[r] & 0x80808080u;
+                    if (h) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if (h & (0x80u << (8 * j))) {
+                                const uint32_t d = ((C[r] >> (8 * j)) & 0xFFu) - ((x[r] >> (8 * j)) & 0xFFu);
+                                const uint32_t t = tbase + 4u * g + j;
+                                if (t < a.n_u) {
+                                    const uint32_t w = list_insert(my_lists + (size_t)r * THREADS * a.k, a.k, (d << IDX_BITS) | t);
+                                    tau[r] = min(tau[r], w);
+                                }
+                            }
+                        }
+                        C[r] = bias_of(tau[r]);
+                    }
+                }
+            }
+        }
+
+        __syncthreads();                                   // every lane is done with this stage
+        if (tid == 0 && c + NSTAGE < c1)
+            issue_chunk(s_t[stage], a.tplanes + (size_t)(c + NSTAGE) * CHUNK, &s_full[stage]);
+        if (++stage == NSTAGE) { stage = 0; parity ^= 1u; }
+    }
+}
+
+// ---- K4: Levenshtein pair scan (Myers bit-parallel, one 32-bit word per pair) -------------------------
+template <int R>
+__global__ void __launch_bounds__(THREADS) knn_leven_scan_kernel(const ScanArgs a) {
+    __shared__ __align__(128) uint2 s_t[NSTAGE][CHUNK];
+    __shared__ __align__(8) uint64_t s_full[NSTAGE];
+
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.y * a.chunks_per_split;
+    const int c1 = min(c0 + a.chunks_per_split, a.n_chunks);
+    if (c0 >= c1) return;
+
+    const int L = a.L;
+    const uint32_t lmask = (1u << L) - 1u;
+    const int64_t qbase = (int64_t)blockIdx.x * (THREADS * R) + tid;
+    uint32_t qlo[R], qhi[R], tau[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int64_t qi = qbase + (int64_t)r * THREADS;
+        const uint2 p = a.qplanes[qi];
+        qlo[r] = p.x;
+        qhi[r] = p.y;
+        uint32_t t = 31u;
+        if (a.warm) t = min((a.warm[(size_t)qi * a.k + (a.k - 1)] >> IDX_BITS) + 1u, 31u);
+        tau[r] = qi < a.q ? t : 0u;
+    }
+    uint32_t *const my_lists = a.lists + ((size_t)blockIdx.y * a.q_pad + qbase) * a.k;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; s++) mbar_init(&s_full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE && c0 + s < c1; s++)
+            issue_chunk(s_t[s], a.tplanes + (size_t)(c0 + s) * CHUNK, &s_full[s]);
+    }
+
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int c = c0; c < c1; c++) {
+        mbar_wait(&s_full[stage], parity);
+        const uint32_t tbase = (uint32_t)c * CHUNK;
+        const int n_here = (int)min((int64_t)CHUNK, a.n_u - (int64_t)tbase);   // skip padding targets
+
+        for (int g = 0; g < n_here; g++) {
+            const uint2 t = s_t[stage][g];                  // warp-uniform target
+            uint32_t Pv[R], Mv[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) { Pv[r] = 0xFFFFFFFFu; Mv[r] = 0u; }
+#pragma unroll 1
+            for (int j = 0; j < L; j++) {
+                const uint32_t LO = 0u - ((t.x >> j) & 1u);  // uniform across the warp
+                const uint32_t HI = 0u - ((t.y >> j) & 1u);
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const uint32_t Eq = ~((qlo[r] ^ LO) | (qhi[r] ^ HI));
+                    const uint32_t Xv = Eq | Mv[r];
+                    const uint32_t Xh = (((Eq & Pv[r]) + Pv[r]) ^ Pv[r]) | Eq;
+                    uint32_t Ph = Mv[r] | ~(Xh | Pv[r]);
+                    uint32_t Mh = Pv[r] & Xh;
+                    Ph = (Ph << 1) | 1u;
+                    Mh = Mh << 1;
+                    Pv[r] = Mh | ~(Xv | Ph);
+                    Mv[r] = Ph & Xv;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const uint32_t d = (uint32_t)(L + __popc(Pv[r] & lmask) - __popc(Mv[r] & lmask));
+                if (d < tau[r]) {
+                    const uint32_t w = list_insert(my_lists + (size_t)r * THREADS * a.k, a.k, (d << IDX_BITS) | (tbase + g));
+                    tau[r] = min(tau[r], w);
+                }
+            }
+        }
+
+        __syncthreads();
+        if (tid == 0 && c + NSTAGE < c1)
+            issue_chunk(s_t[stage], a.tplanes + (size_t)(c + NSTAGE) * CHUNK, &s_full[stage]);
+        if (++stage == NSTAGE) { stage = 0; parity ^= 1u; }
+    }
+}
+
+// ---- merge: k smallest keys over the splits of each query ------------------------------------------------
+__global__ void knn_merge_kernel(const uint32_t *__restrict__ lists, int splits, int64_t q, int64_t q_pad, int k,
+                                 int32_t *__restrict__ out_idx, uint8_t *__restrict__ out_dist, int dist_only) {
+    const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= q) return;
+    uint8_t ptr[MAX_SPLITS];
+    for (int s = 0; s < splits; s++) ptr[s] = 0;
+    for (int j = 0; j < k; j++) {
+        uint32_t best = KEY_EMPTY;
+        int bs = -1;
+        for (int s = 0; s < splits; s++) {
+            if (ptr[s] < k) {
+                const uint32_t v = lists[((size_t)s * q_pad + qi) * k + ptr[s]];
+                if (v < best) { best = v; bs = s; }
+            }
+        }
+        if (bs >= 0) ptr[bs]++;
+        const uint8_t d = best == KEY_EMPTY ? (uint8_t)255 : (uint8_t)(best >> IDX_BITS);
+        if (dist_only) {
+            if (j == 0) out_dist[qi] = d;
+        } else {
+            out_idx[qi * k + j] = best == KEY_EMPTY ? -1 : (int32_t)(best & ((1u << IDX_BITS) - 1u));
+            out_dist[qi * k + j] = d;
+        }
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+
+static int ensure_ws(Index *ix, size_t bytes) {
+    if (bytes <= ix->ws_bytes) return GM_OK;
+    if (ix->ws) {
+        GM_CUDA(cudaDeviceSynchronize());
+        GM_CUDA(cudaFree(ix->ws));
+        ix->ws = nullptr;
+        ix->ws_bytes = 0;
+    }
+    bytes = (bytes + (bytes >> 3) + 4095) & ~(size_t)4095;
+    GM_CUDA(cudaMalloc(&ix->ws, bytes));
+    ix->ws_bytes = bytes;
+    return GM_OK;
+}
+
+template <int R>
+static void launch_scan(int metric, dim3 grid, cudaStream_t st, const ScanArgs &a) {
+    if (metric == GM_METRIC_HAMMING) knn_hamming_scan_kernel<R><<<grid, THREADS, 0, st>>>(a);
+    else knn_leven_scan_kernel<R><<<grid, THREADS, 0, st>>>(a);
+    count_launch();
+}
+
+static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_idx, uint8_t *d_dist, int dist_only,
+                   cudaStream_t st) {
+    GM_ARG(ix && ix->planes, "gm_knn: invalid index handle");
+    GM_ARG(k >= 1 && k <= GM_MAX_K, "gm_knn: k=%d outside [1,%d]", k, GM_MAX_K);
+    GM_ARG(q >= 0, "gm_knn: negative query count");
+    if (q == 0) return GM_OK;
+    GM_ARG(d_q && d_dist && (dist_only || d_idx), "gm_knn: NULL buffer");
+
+    // queries per thread: Levenshtein keeps 2 more state words per pair, so it uses R=4
+    const int R = ix->metric == GM_METRIC_HAMMING ? (g_tune_r == 4 ? 4 : 8) : 4;
+    const int QT = THREADS * R;
+    const int64_t tiles = (q + QT - 1) / QT;
+    const int64_t q_pad = tiles * QT;
+    const int n_chunks = (int)(ix->n_pad / CHUNK);
+
+    // target splits: enough CTAs for >= ~16 per SM so the last wave is a small fraction
+    int splits = g_tune_splits;
+    if (splits <= 0) {
+        const int64_t want = (int64_t)device_sm_count() * 16;
+        splits = (int)((want + tiles - 1) / tiles);
+    }
+    if (splits > n_chunks) splits = n_chunks;
+    if (splits > MAX_SPLITS) splits = MAX_SPLITS;
+    if (splits < 1) splits = 1;
+    int cps = (n_chunks + splits - 1) / splits;
+    splits = (n_chunks + cps - 1) / cps;
+
+    // warm start: worthwhile only when the table is much larger than the sample
+    int warm = g_tune_warm < 0 ? 4 * CHUNK : g_tune_warm;
+    warm = (warm + CHUNK - 1) / CHUNK;                       // in chunks
+    if (n_chunks < 16 * warm || ix->n_u < (int64_t)warm * CHUNK) warm = 0;
+
+    const size_t qp_bytes = (size_t)q_pad * sizeof(uint2);
+    const size_t list_bytes = (size_t)splits * q_pad * k * sizeof(uint32_t);
+    const size_t warm_bytes = warm ? (size_t)q_pad * k * sizeof(uint32_t) : 0;
+    int rc = ensure_ws(ix, qp_bytes + list_bytes + warm_bytes);
+    if (rc) return rc;
+    uint2 *qplanes = reinterpret_cast<uint2 *>(ix->ws);
+    uint32_t *lists = reinterpret_cast<uint32_t *>((char *)ix->ws + qp_bytes);
+    uint32_t *wlists = warm ? reinterpret_cast<uint32_t *>((char *)ix->ws + qp_bytes + list_bytes) : nullptr;
+
+    to_planes_kernel<<<(unsigned)((q_pad + 255) / 256), 256, 0, st>>>(d_q, q, q_pad, qplanes);
+    count_launch();
+    GM_CUDA(cudaMemsetAsync(lists, 0xFF, list_bytes + warm_bytes, st));
+
+    ScanArgs a;
+    a.tplanes = ix->planes;
+    a.n_u = ix->n_u;
+    a.qplanes = qplanes;
+    a.q = q;
+    a.q_pad = q_pad;
+    a.k = k;
+    a.L = ix->L;
+
+    double pairs = 0.0;
+    const int slot = prof_begin(st);
+    if (warm) {
+        a.n_chunks = warm;
+        a.chunks_per_split = warm;
+        a.lists = wlists;
+        a.warm = nullptr;
+        if (R == 8) launch_scan<8>(ix->metric, dim3((unsigned)tiles, 1), st, a);
+        else launch_scan<4>(ix->metric, dim3((unsigned)tiles, 1), st, a);
+        pairs += (double)q * (double)warm * CHUNK;
+    }
+    a.n_chunks = n_chunks;
+    a.chunks_per_split = cps;
+    a.lists = lists;
+    a.warm = wlists;
+    if (R == 8) launch_scan<8>(ix->metric, dim3((unsigned)tiles, (unsigned)splits), st, a);
+    else launch_scan<4>(ix->metric, dim3((unsigned)tiles, (unsigned)splits), st, a);
+    pairs += (double)q * (double)ix->n_u;
+    prof_end(slot, st, pairs);
+
+    knn_merge_kernel<<<(unsigned)((q + 127) / 128), 128, 0, st>>>(lists, splits, q, q_pad, k, d_idx, d_dist, dist_only);
+    count_launch();
+    GM_CUDA(cudaGetLastError());
+    return GM_OK;
+}
+
+}  // namespace gm
+
+using namespace gm;
+
+extern "C" int gm_knn_tune(int queries_per_thread, int splits, int warm_sample) {
+    GM_ARG(queries_per_thread == 0 || queries_per_thread == 4 || queries_per_thread == 8, "gm_knn_tune: queries_per_thread must be 4 or 8");
+    GM_ARG(splits >= 0 && splits <= MAX_SPLITS, "gm_knn_tune: splits outside [0,%d]", MAX_SPLITS);
+    if (queries_per_thread) g_tune_r = queries_per_thread;
+    g_tune_splits = splits;
+    g_tune_warm = warm_sample;
+    return GM_OK;
+}
+
+extern "C" int gm_index_create_dev(const uint64_t *d_uniq2bit, int64_t n_u, int L, int metric, void **index, void *stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    GM_ARG(index, "gm_index_create: NULL handle pointer");
+    *index = nullptr;
+    GM_ARG(d_uniq2bit && n_u >= 1, "gm_index_create: empty guide table");
+    GM_ARG(L >= 1 && L <= GM_MAX_L, "gm_index_create: L=%d outside [1,%d]", L, GM_MAX_L);
+    GM_ARG(metric == GM_METRIC_HAMMING || metric == GM_METRIC_LEVEN, "gm_index_create: unknown metric %d", metric);
+    if (n_u >= (1LL << IDX_BITS)) {
+        set_error("gm_index_create: %lld guides exceed the 2^27 limit of the 32-bit (distance,index) key", (long long)n_u);
+        return GM_ERR_RANGE;
+    }
+    Index *ix = new (std::nothrow) Index();
+    if (!ix) { set_error("out of host memory"); return GM_ERR_NOMEM; }
+    ix->n_u = n_u;
+    ix->n_pad = (n_u + CHUNK - 1) / CHUNK * CHUNK;
+    ix->L = L;
+    ix->metric = metric;
+    cudaError_t e = cudaMalloc(&ix->planes, (size_t)ix->n_pad * sizeof(uint2));
+    if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaMalloc(index)", __FILE__, __LINE__); }
+    cudaStream_t st = (cudaStream_t)stream;
+    to_planes_kernel<<<(unsigned)((ix->n_pad + 255) / 256), 256, 0, st>>>(d_uniq2bit, n_u, ix->n_pad, ix->planes);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaFree(ix->planes); delete ix; return cuda_fail(e, "to_planes_kernel", __FILE__, __LINE__); }
+    *index = ix;
+    return GM_OK;
+}
+
+extern "C" int gm_index_create(const uint64_t *uniq2bit, int64_t n_u, int L, int metric, void **index) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    GM_ARG(index, "gm_index_create: NULL handle pointer");
+    *index = nullptr;
+    GM_ARG(uniq2bit && n_u >= 1, "gm_index_create: empty guide table");
+    uint64_t *d = nullptr;
+    GM_CUDA(cudaMalloc(&d, (size_t)n_u * sizeof(uint64_t)));
+    cudaError_t e = cudaMemcpy(d, uniq2bit, (size_t)n_u * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "cudaMemcpy(H2D guides)", __FILE__, __LINE__); }
+    rc = gm_index_create_dev(d, n_u, L, metric, index, nullptr);
+    cudaError_t e2 = cudaDeviceSynchronize();
+    cudaFree(d);
+    if (rc) return rc;
+    if (e2 != cudaSuccess) { gm_index_free(*index); *index = nullptr; return cuda_fail(e2, "index build", __FILE__, __LINE__); }
+    return GM_OK;
+}
+
+extern "C" int gm_index_info(void *index, int64_t *n_u, int *L, int *metric) {
+    Index *ix = (Index *)index;
+    GM_ARG(ix, "gm_index_info: NULL index");
+    if (n_u) *n_u = ix->n_u;
+    if (L) *L = ix->L;
+    if (metric) *metric = ix->metric;
+    return GM_OK;
+}
+
+extern "C" int gm_index_free(void *index) {
+    Index *ix = (Index *)index;
+    if (!ix) return GM_OK;
+    cudaDeviceSynchronize();
+    if (ix->planes) cudaFree(ix->planes);
+    if (ix->ws) cudaFree(ix->ws);
+    delete ix;
+    return GM_OK;
+}
+
+extern "C" int gm_knn_dev(void *index, const uint64_t *d_q2bit, int64_t q, int k, int32_t *d_out_idx, uint8_t *d_out_dist,
+                          void *stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    return knn_run((Index *)index, d_q2bit, q, k, d_out_idx, d_out_dist, 0, (cudaStream_t)stream);
+}
+
+extern "C" int gm_min_dist_dev(void *index, const uint64_t *d_q2bit, int64_t q, uint8_t *d_out_dist, void *stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    return knn_run((Index *)index, d_q2bit, q, 1, nullptr, d_out_dist, 1, (cudaStream_t)stream);
+}
+
+static int knn_host(void *index, const uint64_t *q2bit, int64_t q, int k, int32_t *out_idx, uint8_t *out_dist, int dist_only) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    GM_ARG(index, "gm_knn: NULL index");
+    GM_ARG(q >= 0, "gm_knn: negative query count");
+    if (q == 0) return GM_OK;
+    GM_ARG(q2bit && out_dist && (dist_only || out_idx), "gm_knn: NULL buffer");
+    GM_ARG(k >= 1 && k <= GM_MAX_K, "gm_knn: k=%d outside [1,%d]", k, GM_MAX_K);
+    uint64_t *d_q = nullptr;
+    int32_t *d_idx = nullptr;
+    uint8_t *d_dist = nullptr;
+    const size_t nd = dist_only ? (size_t)q : (size_t)q * k;
+    cudaError_t e = cudaMalloc(&d_q, (size_t)q * sizeof(uint64_t));
+    if (e == cudaSuccess && !dist_only) e = cudaMalloc(&d_idx, nd * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_dist, nd);
+    if (e == cudaSuccess) e = cudaMemcpy(d_q, q2bit, (size_t)q * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = knn_run((Index *)index, d_q, q, k, d_idx, d_dist, dist_only, nullptr);
+        if (rc == GM_OK) {
+            e = cudaDeviceSynchronize();
+            if (e == cudaSuccess && !dist_only) e = cudaMemcpy(out_idx, d_idx, nd * sizeof(int32_t), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(out_dist, d_dist, nd, cudaMemcpyDeviceToHost);
+        }
+    }
+    cudaFree(d_q);
+    cudaFree(d_idx);
+    cudaFree(d_dist);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "gm_knn", __FILE__, __LINE__);
+    return GM_OK;
+}
+
+extern "C" int gm_knn(void *index, const uint64_t *q2bit, int64_t q, int k, int32_t *out_idx, uint8_t *out_dist) {
+    return knn_host(index, q2bit, q, k, out_idx, out_dist, 0);
+}
+
+extern "C" int gm_min_dist(void *index, const uint64_t *q2bit, int64_t q, uint8_t *out_dist) {
+    return knn_host(index, q2bit, q, 1, nullptr, out_dist, 1);
+}

@@ -1,0 +1,365 @@
+// pam_scan.cu -- K1: IUPAC-degenerate PAM scan over both strands (sm_100a).
+//
+// Replaces the four regex.finditer(..., overlapped=True) generators of PamTarget.find_targets
+// (core.py:142-246) together with their per-hit slicing, reverse-complementing and check_target.
+//
+// Pass 0  encode : ASCII genome (read once, 16-byte vector loads) -> three bit planes lo/hi/valid,
+//                  32 positions per 32-bit word.  Only upper-case A/C/G/T are valid
+//                  (core.py:118-121, :138); everything else (N, lower case, record separators)
+//                  clears the valid bit and can neither match a PAM position nor sit in a target.
+// Pass 1  count  : one thread per 32-position word evaluates BOTH strands for all 32 positions at
+//                  once with bitwise logic: the PAM matches at p iff, for every PAM position j, the
+//                  base at p+j is valid and belongs to the IUPAC set of letter j (a 4-entry truth
+//                  table on the two planes); the target window is accepted iff its L positions are
+//                  valid.  popc of the two hit words -> per-block counts.
+// Pass 2  offsets: exclusive scan of the block counts (forward rows first, then reverse rows).
+// Pass 3  emit   : recomputes the hit words, block-scans the per-thread counts and writes the
+//                  records in ascending position order -- the reference's row order
+//                  (core.py:254-284) -- extracting the L-bit windows with funnel shifts;
+//                  reverse-strand guides are reverse-complemented with brev + bitwise not.
+//
+// Algorithmic HBM bytes: n (ASCII in) + 3n/8 (planes out) + 2 * 3n/8 (planes in, twice) + 14 B per hit.
+#include "common.cuh"
+#include <new>
+
+namespace gm {
+
+static constexpr int SCAN_THREADS = 256;
+
+struct Scan {
+    uint64_t *guides = nullptr;
+    uint32_t *start = nullptr;
+    uint16_t *pamcode = nullptr;
+    int64_t n_fwd = 0, n_rev = 0;
+};
+
+struct PamParams {
+    int P, L, five_prime;
+    int fmask[GM_MAX_PAM];     // IUPAC set of PAM letter j, bit0=A bit1=C bit2=G bit3=T
+    int rmask[GM_MAX_PAM];     // sets of revcomp(PAM) as searched on the forward text (core.py:263,279)
+    int off_f, off_r;          // target window start relative to the match start, per strand
+};
+
+static int iupac_set(char c) {      // core.py:118-121 / :1103-1120
+    switch (c) {
+    case 'A': return 1; case 'C': return 2; case 'G': return 4; case 'T': return 8;
+    case 'M': return 3; case 'R': return 5; case 'W': return 9; case 'S': return 6;
+    case 'Y': return 10; case 'K': return 12; case 'V': return 7; case 'H': return 11;
+    case 'D': return 13; case 'B': return 14; case 'X': return 15; case 'N': return 15;
+    default: return 0;
+    }
+}
+static int complement_set(int m) { return ((m & 1) << 3) | ((m & 2) << 1) | ((m & 4) >> 1) | ((m & 8) >> 3); }
+
+// ---- pass 0 --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS) encode_kernel(const uint8_t *__restrict__ seq, int64_t n_words,
+                                                              uint32_t *__restrict__ lo, uint32_t *__restrict__ hi,
+                                                              uint32_t *__restrict__ valid) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    const uint4 *p = reinterpret_cast<const uint4 *>(seq + w * 32);   // buffer is zero padded to 32 bytes
+    const uint4 a = p[0], b = p[1];
+    const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t l = 0, h = 0, ok = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t c = (v[i] >> (8 * j)) & 0xFFu;
+            const uint32_t good = (c == 'A') | (c == 'C') | (c == 'G') | (c == 'T');
+            const uint32_t x = (c >> 1) & 3u;          // A:0 C:1 G:3 T:2
+            const uint32_t code = x ^ (x >> 1);        // A:0 C:1 G:2 T:3
+            const int bit = 4 * i + j;
+            l |= (code & 1u & good) << bit;
+            h |= ((code >> 1) & good) << bit;
+            ok |= good << bit;
+        }
+    }
+    lo[w + 1] = l;      // word 0 and the words past the end stay zero (= invalid)
+    hi[w + 1] = h;
+    valid[w + 1] = ok;
+}
+
+// ---- window helpers -------------------------------------------------------------------------------------
+// x0..x3 hold positions [32(w-1), 32(w+3)).  bits_at(off) = the 32 positions starting at 32w + off,
+// off in [-32, 64].
+struct Win {
+    uint32_t x0, x1, x2, x3;
+    __device__ __forceinline__ uint32_t at(int off) const {
+        const int a = off + 32, i = a >> 5, sh = a & 31;
+        const uint32_t l = i == 0 ? x0 : i == 1 ? x1 : i == 2 ? x2 : x3;
+        const uint32_t h = i == 0 ? x1 : i == 1 ? x2 : i == 2 ? x3 : 0u;
+        return __funnelshift_r(l, h, sh);
+    }
+};
+
+__device__ __forceinline__ Win load_win(const uint32_t *__restrict__ plane, int64_t w) {
+    Win r;                        // plane[] is stored with one leading zero word
+    r.x0 = plane[w];
+    r.x1 = plane[w + 1];
+    r.x2 = plane[w + 2];
+    r.x3 = plane[w + 3];
+    return r;
+}
+
+__device__ __forceinline__ uint32_t in_set(int set, uint32_t l, uint32_t h) {
+    uint32_t r = 0;
+    if (set & 1) r |= ~h & ~l;
+    if (set & 2) r |= ~h & l;
+    if (set & 4) r |= h & ~l;
+    if (set & 8) r |= h & l;
+    return r;
+}
+
+// hit words of the 32 positions of word w: bit b set <=> a row is emitted for match start 32w+b
+__device__ __forceinline__ void hit_words(const PamParams &pp, const Win &lo, const Win &hi, const Win &va,
+                                          uint32_t &hit_f, uint32_t &hit_r) {
+    uint32_t mf = 0xFFFFFFFFu, mr = 0xFFFFFFFFu;
+    for (int j = 0; j < pp.P; j++) {
+        const uint32_t l = lo.at(j), h = hi.at(j), v = va.at(j);
+        mf &= v & in_set(pp.fmask[j], l, h);
+        mr &= v & in_set(pp.rmask[j], l, h);
+    }
+    uint32_t vf = 0xFFFFFFFFu, vr = 0xFFFFFFFFu;
+    for (int i = 0; i < pp.L; i++) {                 // all L positions of the target window valid
+        vf &= va.at(pp.off_f + i);
+        vr &= va.at(pp.off_r + i);
+    }
+    hit_f = mf & vf;
+    hit_r = mr & vr;
+}
+
+// ---- pass 1 --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS) scan_count_kernel(const PamParams pp, int64_t n_words,
+                                                                  const uint32_t *__restrict__ lo, const uint32_t *__restrict__ hi,
+                                                                  const uint32_t *__restrict__ valid,
+                                                                  uint32_t *__restrict__ blk_f, uint32_t *__restrict__ blk_r) {
+    __shared__ uint32_t s_f[SCAN_THREADS / 32], s_r[SCAN_THREADS / 32];
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t cf = 0, cr = 0;
+    if (w < n_words) {
+        uint32_t hf, hr;
+        hit_words(pp, load_win(lo, w), load_win(hi, w), load_win(valid, w), hf, hr);
+        cf = __popc(hf);
+        cr = __popc(hr);
+    }
+    cf = __reduce_add_sync(0xFFFFFFFFu, cf);
+    cr = __reduce_add_sync(0xFFFFFFFFu, cr);
+    if ((threadIdx.x & 31) == 0) { s_f[threadIdx.x >> 5] = cf; s_r[threadIdx.x >> 5] = cr; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tf = 0, tr = 0;
+        for (int i = 0; i < SCAN_THREADS / 32; i++) { tf += s_f[i]; tr += s_r[i]; }
+        blk_f[blockIdx.x] = tf;
+        blk_r[blockIdx.x] = tr;
+    }
+}
+
+// ---- pass 2: exclusive scan of block counts (single CTA; #blocks = n/8192) ---------------------------------
+__global__ void __launch_bounds__(1024) block_offsets_kernel(int64_t n_blocks, const uint32_t *__restrict__ blk_f,
+                                                             const uint32_t *__restrict__ blk_r, uint64_t *__restrict__ off_f,
+                                                             uint64_t *__restrict__ off_r, uint64_t *__restrict__ totals) {
+    __shared__ uint64_t s_w[2][32];
+    __shared__ uint64_t s_carry[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_carry[0] = 0; s_carry[1] = 0; }
+    __syncthreads();
+    for (int64_t base = 0; base < n_blocks; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        uint64_t vf = i < n_blocks ? blk_f[i] : 0, vr = i < n_blocks ? blk_r[i] : 0;
+        uint64_t sf = vf, sr = vr;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t tf = __shfl_up_sync(0xFFFFFFFFu, sf, d), tr = __shfl_up_sync(0xFFFFFFFFu, sr, d);
+            if (lane >= d) { sf += tf; sr += tr; }
+        }
+        if (lane == 31) { s_w[0][warp] = sf; s_w[1][warp] = sr; }
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t wf = s_w[0][lane], wr = s_w[1][lane];
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t tf = __shfl_up_sync(0xFFFFFFFFu, wf, d), tr = __shfl_up_sync(0xFFFFFFFFu, wr, d);
+                if (lane >= d) { wf += tf; wr += tr; }
+            }
+            s_w[0][lane] = wf;
+            s_w[1][lane] = wr;
+        }
+        __syncthreads();
+        const uint64_t pf = s_carry[0] + (warp ? s_w[0][warp - 1] : 0) + sf - vf;
+        const uint64_t pr = s_carry[1] + (warp ? s_w[1][warp - 1] : 0) + sr - vr;
+        if (i < n_blocks) { off_f[i] = pf; off_r[i] = pr; }
+        __syncthreads();
+        if (threadIdx.x == 1023) { s_carry[0] += s_w[0][31]; s_carry[1] += s_w[1][31]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { totals[0] = s_carry[0]; totals[1] = s_carry[1]; }
+}
+
+// ---- pass 3 --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bit_reverse_low(uint32_t x, int nbits) { return __brev(x) >> (32 - nbits); }
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_emit_kernel(const PamParams pp, int64_t n_words,
+                                                                 const uint32_t *__restrict__ lo, const uint32_t *__restrict__ hi,
+                                                                 const uint32_t *__restrict__ valid,
+                                                                 const uint64_t *__restrict__ off_f, const uint64_t *__restrict__ off_r,
+                                                                 uint64_t n_fwd_total, uint64_t *__restrict__ guides,
+                                                                 uint32_t *__restrict__ start, uint16_t *__restrict__ pamcode) {
+    __shared__ uint32_t s_f[SCAN_THREADS / 32], s_r[SCAN_THREADS / 32];
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t hf = 0, hr = 0;
+    Win wl, wh;
+    wl.x0 = wl.x1 = wl.x2 = wl.x3 = 0;
+    wh = wl;
+    if (w < n_words) {
+        wl = load_win(lo, w);
+        wh = load_win(hi, w);
+        hit_words(pp, wl, wh, load_win(valid, w), hf, hr);
+    }
+    const uint32_t cf = __popc(hf), cr = __popc(hr);
+    uint32_t sf = cf, sr = cr;                       // inclusive warp scans
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t tf = __shfl_up_sync(0xFFFFFFFFu, sf, d), tr = __shfl_up_sync(0xFFFFFFFFu, sr, d);
+        if (lane >= d) { sf += tf; sr += tr; }
+    }
+    if (lane == 31) { s_f[warp] = sf; s_r[warp] = sr; }
+    __syncthreads();
+    uint32_t wf = 0, wr = 0;
+    for (int i = 0; i < warp; i++) { wf += s_f[i]; wr += s_r[i]; }
+    uint64_t out_f = off_f[blockIdx.x] + wf + sf - cf;
+    uint64_t out_r = n_fwd_total + off_r[blockIdx.x] + wr + sr - cr;
+
+    const uint32_t lmask = (1u << pp.L) - 1u, pmask = (1u << pp.P) - 1u;
+    const int64_t pos0 = w * 32;
+    while (hf) {                                     // forward-strand rows, ascending position
+        const int b = __ffs(hf) - 1;
+        hf &= hf - 1;
+        const uint32_t gl = wl.at(b + pp.off_f) & lmask, gh = wh.at(b + pp.off_f) & lmask;
+        const uint32_t pl = wl.at(b) & pmask, ph = wh.at(b) & pmask;
+        guides[out_f] = from_planes(gl, gh);
+        start[out_f] = (uint32_t)(pos0 + b + pp.off_f);
+        pamcode[out_f] = (uint16_t)from_planes(pl, ph);
+        out_f++;
+    }
+    while (hr) {                                     // reverse-strand rows: reverse complement
+        const int b = __ffs(hr) - 1;
+        hr &= hr - 1;
+        const uint32_t gl = bit_reverse_low(~wl.at(b + pp.off_r) & lmask, pp.L);
+        const uint32_t gh = bit_reverse_low(~wh.at(b + pp.off_r) & lmask, pp.L);
+        const uint32_t pl = bit_reverse_low(~wl.at(b) & pmask, pp.P);
+        const uint32_t ph = bit_reverse_low(~wh.at(b) & pmask, pp.P);
+        guides[out_r] = from_planes(gl, gh);
+        start[out_r] = (uint32_t)(pos0 + b + pp.off_r);
+        pamcode[out_r] = (uint16_t)from_planes(pl, ph);
+        out_r++;
+    }
+}
+
+}  // namespace gm
+
+using namespace gm;
+
+extern "C" int gm_scan_free(void *scan) {
+    Scan *s = (Scan *)scan;
+    if (!s) return GM_OK;
+    cudaFree(s->guides);
+    cudaFree(s->start);
+    cudaFree(s->pamcode);
+    delete s;
+    return GM_OK;
+}
+
+extern "C" int gm_scan_create(const uint8_t *seq_ascii, int64_t n, const char *pam, int pam_len, int five_prime, int L,
+                              void **scan, int64_t *n_fwd, int64_t *n_rev) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    GM_ARG(scan && n_fwd && n_rev, "gm_scan_create: NULL output pointer");
+    *scan = nullptr;
+    *n_fwd = *n_rev = 0;
+    GM_ARG(n >= 0 && (n == 0 || seq_ascii), "gm_scan_create: bad sequence buffer");
+    GM_ARG(pam && pam_len >= 1 && pam_len <= GM_MAX_PAM, "gm_scan_create: PAM length %d outside [1,%d]", pam_len, GM_MAX_PAM);
+    GM_ARG(L >= 1 && L <= GM_MAX_L, "gm_scan_create: L=%d outside [1,%d]", L, GM_MAX_L);
+    if (n > 0xFFFFFF00LL) { set_error("gm_scan_create: %lld bases exceed the uint32 coordinate range", (long long)n); return GM_ERR_RANGE; }
+
+    PamParams pp;
+    memset(&pp, 0, sizeof pp);
+    pp.P = pam_len;
+    pp.L = L;
+    pp.five_prime = five_prime ? 1 : 0;
+    for (int j = 0; j < pam_len; j++) {
+        pp.fmask[j] = iupac_set(pam[j]);
+        GM_ARG(pp.fmask[j] != 0, "gm_scan_create: '%c' is not an IUPAC letter", pam[j]);
+    }
+    for (int j = 0; j < pam_len; j++) pp.rmask[j] = complement_set(pp.fmask[pam_len - 1 - j]);
+    // target window relative to the match start ms (me = ms + P): core.py:155,183,209,236
+    pp.off_f = five_prime ? pam_len : -L;
+    pp.off_r = five_prime ? -L : pam_len;
+
+    Scan *s = new (std::nothrow) Scan();
+    if (!s) { set_error("out of host memory"); return GM_ERR_NOMEM; }
+    *scan = s;
+    if (n == 0) return GM_OK;
+
+    const int64_t n_words = (n + 31) / 32;
+    const int64_t n_blocks = (n_words + SCAN_THREADS - 1) / SCAN_THREADS;
+    const size_t plane_words = (size_t)n_words + 4;
+    uint8_t *d_seq = nullptr;
+    uint32_t *d_planes = nullptr, *d_blk = nullptr;
+    uint64_t *d_off = nullptr;
+    uint64_t totals[2] = {0, 0};
+    cudaError_t e = cudaMalloc(&d_seq, (size_t)n_words * 32);
+    if (e == cudaSuccess) e = cudaMalloc(&d_planes, 3 * plane_words * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_blk, (size_t)n_blocks * 2 * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_off, ((size_t)n_blocks * 2 + 2) * 8);
+    if (e == cudaSuccess) e = cudaMemset(d_seq + (n_words - 1) * 32, 0, 32);
+    if (e == cudaSuccess) e = cudaMemcpy(d_seq, seq_ascii, (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_planes, 0, 3 * plane_words * 4);
+    uint32_t *lo = d_planes, *hi = d_planes + plane_words, *va = d_planes + 2 * plane_words;
+    uint32_t *blk_f = d_blk, *blk_r = d_blk + n_blocks;
+    uint64_t *off_f = d_off, *off_r = d_off + n_blocks, *d_tot = d_off + 2 * n_blocks;
+    if (e == cudaSuccess) {
+        encode_kernel<<<(unsigned)n_blocks, SCAN_THREADS>>>(d_seq, n_words, lo, hi, va);
+        scan_count_kernel<<<(unsigned)n_blocks, SCAN_THREADS>>>(pp, n_words, lo, hi, va, blk_f, blk_r);
+        block_offsets_kernel<<<1, 1024>>>(n_blocks, blk_f, blk_r, off_f, off_r, d_tot);
+        count_launch(3);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(totals, d_tot, sizeof totals, cudaMemcpyDeviceToHost);
+    const int64_t nf = (int64_t)totals[0], nr = (int64_t)totals[1], nt = nf + nr;
+    if (e == cudaSuccess && nt > 0) {
+        e = cudaMalloc(&s->guides, (size_t)nt * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&s->start, (size_t)nt * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&s->pamcode, (size_t)nt * 2);
+        if (e == cudaSuccess) {
+            scan_emit_kernel<<<(unsigned)n_blocks, SCAN_THREADS>>>(pp, n_words, lo, hi, va, off_f, off_r, (uint64_t)nf,
+                                                                   s->guides, s->start, s->pamcode);
+            count_launch();
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
+    cudaFree(d_seq);
+    cudaFree(d_planes);
+    cudaFree(d_blk);
+    cudaFree(d_off);
+    if (e != cudaSuccess) {
+        gm_scan_free(s);
+        *scan = nullptr;
+        return cuda_fail(e, "gm_scan_create", __FILE__, __LINE__);
+    }
+    s->n_fwd = nf;
+    s->n_rev = nr;
+    *n_fwd = nf;
+    *n_rev = nr;
+    return GM_OK;
+}
+
+extern "C" int gm_scan_fetch(void *scan, uint64_t *guide2bit, uint32_t *start, uint16_t *pamcode) {
+    Scan *s = (Scan *)scan;
+    GM_ARG(s, "gm_scan_fetch: NULL handle");
+    const size_t nt = (size_t)(s->n_fwd + s->n_rev);
+    if (nt == 0) return GM_OK;
+    if (guide2bit) GM_CUDA(cudaMemcpy(guide2bit, s->guides, nt * 8, cudaMemcpyDeviceToHost));
+    if (start) GM_CUDA(cudaMemcpy(start, s->start, nt * 4, cudaMemcpyDeviceToHost));
+    if (pamcode) GM_CUDA(cudaMemcpy(pamcode, s->pamcode, nt * 2, cudaMemcpyDeviceToHost));
+    return GM_OK;
+}

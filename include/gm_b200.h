@@ -1,0 +1,125 @@
+/*
+ * gm_b200.h -- C ABI of libgm_b200.so: the B200 (sm_100a) engine behind GuideMaker's off-target
+ * hot path.  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * The reference (USDA-ARS-GBRU/GuideMaker, pure Python) has no FFI of its own for this path: its
+ * four hot methods call three third-party native engines.  Each entry point below replaces one
+ * of those call sites (file:line in /root/reference/guidemaker/core.py):
+ *
+ *   gm_scan_*            regex.finditer(pam_regex, seq, overlapped=True) + slicing/revcomp/
+ *                        check_target                                   core.py:142-246 (call sites :154,:182,:207,:234)
+ *   gm_seed_dedup        Series.duplicated() over the seed strings      core.py:402-416
+ *   gm_first_occurrence  list(set(targets))  (made deterministic: first-occurrence order) core.py:446
+ *   gm_index_create      nmslib.init + addDataPointBatch + createIndex  core.py:451-457, :461-467
+ *   gm_knn               index.knnQueryBatch(queries, k=knum)           core.py:502-503
+ *   gm_min_dist          index.knnQueryBatch(binseq, k=2) -> i[1][0]    core.py:603-606
+ *
+ * Conventions
+ *   - "guide2bit": one guide per uint64, base i (0 = 5'-most) in bits [2i,2i+1], A=0 C=1 G=2 T=3,
+ *     1 <= L <= 27.
+ *   - Every function returns GM_OK (0) or a negative GM_ERR_* code; gm_last_error() gives the
+ *     message (thread-local).  Nothing throws across the ABI.
+ *   - The caller owns every buffer it passes; the library owns only what is behind its opaque
+ *     handles (freed by the matching *_free).  Host-pointer calls are synchronous on return.
+ *   - *_dev variants take DEVICE pointers and enqueue on the given cudaStream_t (passed as
+ *     void*, NULL = default stream) without synchronising; they exist for HBM-resident
+ *     pipelines (bench `value`, multi-GPU sharding over torch.distributed/NCCL buffers).
+ *   - Distances are true mismatch / edit counts (NOT doubled as nmslib's one-hot bit_hamming).
+ *     Neighbours are ordered ascending by (distance, target index); rows with fewer than k
+ *     targets are padded with idx = -1, dist = 255.
+ *   - There is no CPU fallback: without a CUDA device of compute capability 10.x gm_init fails.
+ */
+#ifndef GM_B200_H
+#define GM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GM_OK          0
+#define GM_ERR_CUDA   -1   /* a CUDA runtime call or kernel failed            */
+#define GM_ERR_ARG    -2   /* invalid argument (bad PAM letter, L, k, NULL)   */
+#define GM_ERR_NOMEM  -3   /* host or device allocation failed               */
+#define GM_ERR_NODEV  -4   /* no usable sm_100 device                        */
+#define GM_ERR_RANGE  -5   /* input exceeds a documented limit               */
+
+#define GM_METRIC_HAMMING 0
+#define GM_METRIC_LEVEN   1
+
+#define GM_MAX_L    27      /* cli.py:43  guidelength 10..27 (one 32-bit plane per guide) */
+#define GM_MAX_K    32      /* cli.py:55  knum 2..20                                      */
+#define GM_MAX_PAM  8       /* cli.py:84  PAM length 2..8                                 */
+
+/* ---- library ------------------------------------------------------------------------------- */
+int         gm_init(int device);              /* select device, check sm_100, warm the context   */
+const char *gm_last_error(void);
+int         gm_version(void);
+/* sm_count, compute capability and total HBM of the device chosen by gm_init */
+int         gm_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *mem_bytes);
+
+/* ---- K1: IUPAC PAM scan over both strands ------------------------------------------------------
+ * seq_ascii: n bytes of one record (or several records joined by any non-ACGT byte).  Only
+ * upper-case A/C/G/T match a PAM position or are allowed inside a target (core.py:118-121,:138).
+ * Rows come out forward-strand hits first (ascending position), then reverse-strand hits
+ * (ascending position) -- the reference's row order (core.py:254-284).
+ * gm_scan_fetch fills, for n_fwd + n_rev rows: the guide as it appears in the `target` column
+ * (reverse hits reverse-complemented), the 0-based forward-strand start of the target window,
+ * and exact_pam packed 2 bits/base (PAM base j in bits [2j,2j+1], reverse hits
+ * reverse-complemented).  Any output pointer may be NULL. */
+int gm_scan_create(const uint8_t *seq_ascii, int64_t n, const char *pam, int pam_len,
+                   int five_prime, int L, void **scan, int64_t *n_fwd, int64_t *n_rev);
+int gm_scan_fetch(void *scan, uint64_t *guide2bit, uint32_t *start, uint16_t *pamcode);
+int gm_scan_free(void *scan);
+
+/* ---- K2: keep-first duplicate flags -----------------------------------------------------------
+ * is_dup[i] = 1 iff an earlier row has the same seed (first lsr bases if five_prime, last lsr
+ * bases otherwise, the whole guide if lsr == 0) -- pandas duplicated(keep='first'). */
+int gm_seed_dedup(const uint64_t *guide2bit, int64_t n, int L, int lsr, int five_prime,
+                  uint8_t *is_dup);
+/* first_row[i] = smallest row whose key equals keys[i] (distinct guides in first-occurrence
+ * order are the rows with first_row[i] == i). n < 2^31. */
+int gm_first_occurrence(const uint64_t *keys, int64_t n, int64_t *first_row);
+
+/* ---- K3/K4/K5: exact brute-force kNN index -----------------------------------------------------
+ * The index is the table of distinct guides resident in HBM (bit-plane layout).
+ * n_u < 2^27. */
+int gm_index_create(const uint64_t *uniq2bit, int64_t n_u, int L, int metric, void **index);
+int gm_index_create_dev(const uint64_t *d_uniq2bit, int64_t n_u, int L, int metric, void **index,
+                        void *stream);
+int gm_index_info(void *index, int64_t *n_u, int *L, int *metric);
+int gm_index_free(void *index);
+
+/* out_idx: q*k int32, out_dist: q*k uint8, row-major */
+int gm_knn(void *index, const uint64_t *q2bit, int64_t q, int k, int32_t *out_idx,
+           uint8_t *out_dist);
+int gm_knn_dev(void *index, const uint64_t *d_q2bit, int64_t q, int k, int32_t *d_out_idx,
+               uint8_t *d_out_dist, void *stream);
+/* distance to the nearest indexed guide */
+int gm_min_dist(void *index, const uint64_t *q2bit, int64_t q, uint8_t *out_dist);
+int gm_min_dist_dev(void *index, const uint64_t *d_q2bit, int64_t q, uint8_t *d_out_dist,
+                    void *stream);
+
+/* ---- measurement hooks ---------------------------------------------------------------------------
+ * With profiling on, the library brackets its dominant kernel (the pair-scan of gm_knn*) with
+ * CUDA events on the launching stream.  gm_prof_read synchronises those events and returns the
+ * accumulated kernel time, the number of those launches, the (query, target) pairs they
+ * evaluated, and the total number of kernels of this library launched since gm_prof_reset. */
+int gm_prof_enable(int on);
+int gm_prof_reset(void);
+int gm_prof_read(double *scan_kernel_ms, int64_t *scan_kernel_launches, double *pairs,
+                 int64_t *all_kernel_launches);
+
+/* tuning knob for experiments and tests: queries per thread (4 or 8), target splits (0 = auto),
+ * warm-start sample size (0 = off, -1 = default) */
+int gm_knn_tune(int queries_per_thread, int splits, int warm_sample);
+
+/* register-resident microbenchmarks used as roofline denominators:
+ * what = 0: POPC, 1: LOP3, 2: IMAD.  Returns lane-operations per second over the whole GPU. */
+int gm_microbench(int what, double *ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GM_B200_H */

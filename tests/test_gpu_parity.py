@@ -1,0 +1,269 @@
+"""GPU parity tests: every kernel of libgm_b200.so, called through the C ABI (ctypes), against the
+CPU oracle on the same seeded inputs and against the committed reference fixtures.  Bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from guidemaker_b200 import _capi
+    _capi.init(0)
+    yield _capi
+    _capi.knn_tune(8, 0, -1)
+
+
+def rand_guides(rng, n, L, n_base=None):
+    """random guides with planted duplicates and near-duplicates (ties, small distances)"""
+    n_base = n_base or max(n // 2, 1)
+    base = rng.integers(0, 4, size=(n_base, L), dtype=np.uint64)
+    rows = base[rng.integers(0, n_base, size=n)]
+    mut = rng.random(n) < 0.5
+    pos = rng.integers(0, L, size=n)
+    rows[mut, pos[mut]] = rng.integers(0, 4, size=int(mut.sum()), dtype=np.uint64)
+    g = np.zeros(n, dtype=np.uint64)
+    for i in range(L):
+        g |= rows[:, i] << np.uint64(2 * i)
+    return g
+
+
+def rand_genome(rng, n, gc=0.5, n_frac=0.002, lower_frac=0.001):
+    s = rng.choice(np.frombuffer(b"GCAT", np.uint8), size=n, p=[gc / 2, gc / 2, (1 - gc) / 2, (1 - gc) / 2])
+    k = int(n * n_frac)
+    if k:
+        for st in rng.integers(0, max(n - 8, 1), size=max(k // 4, 1)):
+            s[st:st + rng.integers(1, 8)] = ord("N")
+    k = int(n * lower_frac)
+    if k:
+        idx = rng.integers(0, n, size=k)
+        s[idx] = s[idx] + 32
+    return s.tobytes()
+
+
+# ---- K1 ---------------------------------------------------------------------------------------------------
+CASES = {"ngg3p20": ("NGG", False, 20), "ngg5p20": ("NGG", True, 20), "tttv5p23": ("TTTV", True, 23), "nngrrt3p21": ("NNGRRT", False, 21)}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_scan_carsonella_vs_oracle_and_reference(capi, name, carsonella, carsonella_ref):
+    pam, five, L = CASES[name]
+    seq = carsonella[1].encode()
+    g, s, p, nf, nr = capi.pam_scan(seq, pam, five, L)
+    og, os_, op, onf, onr = O.c_pam_scan(seq, pam, five, L)
+    assert (nf, nr) == (onf, onr)
+    assert np.array_equal(g, og) and np.array_equal(s, os_) and np.array_equal(p, op)
+    r = carsonella_ref
+    assert np.array_equal(np.array([O.unpack(v, L) for v in g], dtype="S"), r[name + "/target"])
+    assert np.array_equal(s, r[name + "/start"])
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_scan_random_iupac(capi, seed):
+    rng = np.random.default_rng(seed)
+    letters = list("ACGTMRWSYKVHDBXN")
+    for _ in range(6):
+        P = int(rng.integers(1, 9)); L = int(rng.integers(1, 28)); five = bool(rng.integers(2))
+        pam = "".join(rng.choice(letters, size=P, p=[0.12] * 4 + [0.52 / 12] * 12))
+        n = int(rng.choice([0, 1, 5, 31, 32, 33, 63, 64, 65, 200, 1000, 8191, 8192, 8193, 50000]))
+        seq = rand_genome(rng, n, gc=float(rng.uniform(0.2, 0.8)), n_frac=0.01) if n else b""
+        got = capi.pam_scan(seq, pam, five, L)
+        exp = O.c_pam_scan(seq, pam, five, L)
+        assert got[3:] == exp[3:], (pam, five, L, n)
+        for a, b in zip(got[:3], exp[:3]):
+            assert np.array_equal(a, b), (pam, five, L, n)
+
+
+def test_scan_hits_at_record_ends(capi):
+    L = 20
+    core = "ACGTACGTACGTACGTACGT"
+    for seq in ("CCA" + core + "TGG", core + "AGG", "CCT" + core, "GG" + core[:18] + "CC", "NGG" + core + "NGG" + "N" * 40 + "CCN" + core):
+        for five in (False, True):
+            got = capi.pam_scan(seq.encode(), "NGG", five, L)
+            exp = O.c_pam_scan(seq.encode(), "NGG", five, L)
+            assert got[3:] == exp[3:]
+            for a, b in zip(got[:3], exp[:3]):
+                assert np.array_equal(a, b)
+
+
+def test_scan_rejects_bad_pam(capi):
+    with pytest.raises(ValueError):
+        capi.pam_scan(b"ACGT" * 10, "NGZ", False, 20)
+    with pytest.raises(ValueError):
+        capi.pam_scan(b"ACGT" * 10, "NGG", False, 28)
+
+
+# ---- K2 ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(4))
+def test_seed_dedup_vs_oracle(capi, seed):
+    rng = np.random.default_rng(10 + seed)
+    for n in (1, 2, 1000, 100003):
+        L = int(rng.integers(10, 28)); lsr = int(rng.integers(0, L + 1)); five = bool(rng.integers(2))
+        g = rand_guides(rng, n, L, n_base=max(n // 8, 1))
+        assert np.array_equal(capi.seed_dedup(g, L, lsr, five), O.c_seed_dedup(g, L, lsr, five))
+        assert np.array_equal(capi.first_occurrence(g), O.c_first_occurrence(g))
+    assert len(capi.seed_dedup(np.zeros(0, np.uint64), 20, 10, False)) == 0
+
+
+def test_dedup_all_equal_and_all_distinct(capi):
+    g = np.full(5000, 12345, np.uint64)
+    d = capi.seed_dedup(g, 20, 10, True)
+    assert not d[0] and d[1:].all()
+    g = np.arange(5000, dtype=np.uint64) << np.uint64(20)
+    assert not capi.seed_dedup(g, 20, 0, True).any()
+    assert capi.seed_dedup(g, 20, 10, True)[1:].all()          # first 10 bases all 'A' -> every later row is a duplicate
+
+
+# ---- K3a / K5 ----------------------------------------------------------------------------------------------
+def check_knn(capi, targets, queries, L, metric, k):
+    ix = capi.Index(targets, L, metric)
+    idx, dist = ix.knn(queries, k)
+    oi, od = O.c_knn(targets, queries, L, metric, k)
+    assert np.array_equal(dist, od)
+    assert np.array_equal(idx, oi)
+    md = ix.min_dist(queries)
+    assert np.array_equal(md, od[:, 0])
+    ix.close()
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 20, 32])
+def test_knn_hamming_carsonella_all_vs_all(capi, k, carsonella):
+    g, *_ = O.c_pam_scan(carsonella[1].encode(), "NGG", False, 20)
+    uniq, _ = O.unique_first_order(g)
+    check_knn(capi, uniq, g, 20, 0, k)
+
+
+@pytest.mark.parametrize("L", [1, 10, 16, 17, 20, 27])
+def test_knn_hamming_lengths_and_ragged_sizes(capi, L):
+    rng = np.random.default_rng(L)
+    for n_t, n_q in ((1, 1), (3, 7), (1023, 1025), (1024, 4096), (1025, 100), (5000, 3333)):
+        t, _ = O.unique_first_order(rand_guides(rng, n_t, L))
+        q = rand_guides(rng, n_q, L)
+        check_knn(capi, t, q, L, 0, 5)
+
+
+def test_knn_fewer_targets_than_k(capi):
+    rng = np.random.default_rng(3)
+    t, _ = O.unique_first_order(rand_guides(rng, 4, 20))
+    ix = capi.Index(t, 20, 0)
+    idx, dist = ix.knn(t, 8)
+    assert (idx[:, len(t):] == -1).all() and (dist[:, len(t):] == 255).all()
+    oi, od = O.c_knn(t, t, 20, 0, 8)
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+
+
+def test_knn_ties_resolved_by_index(capi):
+    # every target at distance exactly 1 from the query: ties everywhere -> lowest indices win
+    L = 20
+    q = O.pack("A" * L)
+    t = []
+    for pos in range(L):
+        for b in "CGT":
+            s = ["A"] * L; s[pos] = b; t.append("".join(s))
+    t = O.pack_many(t)
+    ix = capi.Index(t, L, 0)
+    idx, dist = ix.knn(np.array([q], np.uint64), 10)
+    assert idx[0].tolist() == list(range(10)) and (dist[0] == 1).all()
+    check_knn(capi, np.tile(t, 1)[::-1].copy(), np.array([q] * 300, np.uint64), L, 0, 7)
+
+
+@pytest.mark.parametrize("tune", [(4, 0, -1), (8, 1, 0), (8, 3, 0), (4, 7, 2048), (8, 64, 1024), (8, 0, 4096)])
+def test_knn_hamming_tuning_variants_agree(capi, tune):
+    """queries per thread, target splits and warm start must not change a single bit"""
+    rng = np.random.default_rng(99)
+    t, _ = O.unique_first_order(rand_guides(rng, 70000, 20, n_base=60000))
+    q = rand_guides(rng, 3000, 20)
+    capi.knn_tune(*tune)
+    try:
+        check_knn(capi, t, q, 20, 0, 6)
+    finally:
+        capi.knn_tune(8, 0, -1)
+
+
+# ---- K4 ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L", [10, 20, 23, 27])
+def test_knn_leven_vs_oracle(capi, L):
+    rng = np.random.default_rng(40 + L)
+    t, _ = O.unique_first_order(rand_guides(rng, 3000, L))
+    # queries: targets with an insertion/deletion (shifted) so edit distance < hamming distance
+    q = rand_guides(rng, 700, L)
+    sh = t[rng.integers(0, len(t), size=300)]
+    mask = np.uint64((1 << (2 * L)) - 1)
+    q = np.concatenate([q, (sh << np.uint64(2)) & mask, sh >> np.uint64(2)])
+    check_knn(capi, t, q, L, 1, 4)
+
+
+def test_knn_leven_inline_reference_vector(capi, inline_ref):
+    """tests/test_core.py:319-347 -- leven [0,1,2], hamming [0,1,16]"""
+    seq = inline_ref["lev/seq"][0]
+    g, *_ = capi.pam_scan(seq, "NGG", False, 20)
+    uniq = g[np.sort(np.unique(g, return_index=True)[1])]
+    qi = [O.unpack(v, 20) for v in uniq].index("CTAGTCACTAGCTGACAGCA")
+    assert capi.Index(uniq, 20, 1).knn(uniq, 3)[1][qi].tolist() == [0, 1, 2]
+    assert capi.Index(uniq, 20, 0).knn(uniq, 3)[1][qi].tolist() == [0, 1, 16]
+
+
+def test_knn_leven_warm_and_splits(capi):
+    rng = np.random.default_rng(5)
+    t, _ = O.unique_first_order(rand_guides(rng, 40000, 23, n_base=30000))
+    q = rand_guides(rng, 600, 23)
+    for tune in ((8, 5, 2048), (8, 1, 0)):
+        capi.knn_tune(*tune)
+        try:
+            check_knn(capi, t, q, 23, 1, 3)
+        finally:
+            capi.knn_tune(8, 0, -1)
+
+
+# ---- errors ---------------------------------------------------------------------------------------------------
+def test_argument_errors(capi):
+    with pytest.raises(ValueError):
+        capi.Index(np.zeros(0, np.uint64), 20, 0)
+    with pytest.raises(ValueError):
+        capi.Index(np.zeros(4, np.uint64), 28, 0)
+    ix = capi.Index(np.arange(4, dtype=np.uint64), 20, 0)
+    with pytest.raises(ValueError):
+        ix.knn(np.zeros(3, np.uint64), 33)
+    assert ix.knn(np.zeros(0, np.uint64), 3)[0].shape == (0, 3)
+
+
+# ---- BASELINE-size property checks ---------------------------------------------------------------------------
+def test_knn_hamming_config2_scale_properties(capi):
+    """configs[1] scale (6.3 Mb, 66 % GC, NGG 3prime, L=20): sample-checked against the oracle plus
+    size-independent properties over all rows."""
+    rng = np.random.default_rng(2)
+    seq = rand_genome(rng, 6_300_000, gc=0.66, n_frac=0.0005, lower_frac=0)
+    g, s, p, nf, nr = capi.pam_scan(seq, "NGG", False, 20)
+    assert 1.0e6 < len(g) < 1.8e6
+    first = capi.first_occurrence(g)
+    is_first = first == np.arange(len(g))
+    uniq = np.ascontiguousarray(g[is_first])
+    row2uniq = (np.cumsum(is_first) - 1)[first]
+    ix = capi.Index(uniq, 20, 0)
+    k = 5
+    idx, dist = ix.knn(g, k)
+    # (1) the self hit comes first, at distance 0 and at the query's own index
+    assert (dist[:, 0] == 0).all() and np.array_equal(idx[:, 0], row2uniq.astype(np.int32))
+    # (2) rows are sorted by (distance, index), indices distinct and in range
+    key = dist.astype(np.int64) * (1 << 32) + idx
+    assert (np.diff(key, axis=1) > 0).all() and idx.min() >= 0 and idx.max() < len(uniq)
+    # (3) reported distances are the true distances of the reported pairs
+    def ham(a, b):
+        x = a ^ b
+        x = (x | (x >> np.uint64(1))) & np.uint64(0x5555555555555555)
+        return np.array([bin(int(v)).count("1") for v in x])
+    rows = rng.integers(0, len(g), size=2000)
+    for j in range(k):
+        assert np.array_equal(ham(g[rows], uniq[idx[rows, j]]), dist[rows, j])
+    # (4) oracle on a random sample of queries against the whole table
+    rows = rng.integers(0, len(g), size=512)
+    oi, od = O.c_knn(uniq, g[rows], 20, 0, k)
+    assert np.array_equal(idx[rows], oi) and np.array_equal(dist[rows], od)
+    # (5) min-distance query == first column
+    assert np.array_equal(ix.min_dist(g[:100000]), dist[:100000, 0])
+    # (6) scan + dedupe agree with the oracle at full size
+    og, os_, op, onf, onr = O.c_pam_scan(seq, "NGG", False, 20)
+    assert np.array_equal(g, og) and np.array_equal(s, os_) and (nf, nr) == (onf, onr)
+    assert np.array_equal(capi.seed_dedup(g, 20, 10, False), O.c_seed_dedup(g, 20, 10, False))
