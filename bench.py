@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the off-target hot path (BASELINE.json: "off-target comparisons/s
+(20-nt Hamming kNN) + genome wall-time").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --gpus N ...            # CPU arm: exact brute force on the host cores
+
+One STEP = one exact all-vs-all kNN pass (every PAM target row against the table of distinct guides,
+k = 5) over the workload of BASELINE.json configs[1]: a synthetic 6.3 Mb, 66 %-GC bacterial genome,
+PAM NGG 3prime, 20-nt guides, Hamming.  A comparison = one (query, indexed guide) distance evaluation;
+a step performs Q x N_u of them.
+
+  value    comparisons/s with queries and the guide table already resident in HBM (gm_knn_dev on torch's
+           current stream), K steps timed with CUDA events between barrier + synchronize, max over ranks.
+           N > 1: the table is replicated, query rows are sharded over the ranks and the per-rank top-k is
+           all-gathered with NCCL inside the timed region; the workload is the same for every N (strong).
+  e2e      the same metric through the host-buffer C ABI (gm_index_create + gm_knn via ctypes): every step
+           copies the guide table and that step's queries host->device from pinned memory and reads the
+           (idx, dist) result device->host.
+  roofline the pair-scan kernel (the dominant kernel) against the measured POPC-pipe rate of this GPU.
+  cpu_baseline  the CPU oracle port (oracle/gm_oracle.c, exact brute force, OpenMP over all host cores) on
+           a bounded sample of the same workload.
+
+The reference arm times that same CPU brute force as its whole measurement: the reference's own engine
+(nmslib 2.1.1 HNSW) is a third-party package absent from this image and from /opt/wheelhouse, so the
+oracle port -- the published definition of the search nmslib approximates -- stands in.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "off-target comparisons/s (20-nt Hamming kNN)"
+UNIT = "comparisons/s"
+WORKLOAD = "c2_bacterial_6.3Mb"
+K_NEIGHBORS = 5
+GUIDE_LEN = 20
+PUBLISHED_REF_BRUTEFORCE = 2.17e8      # tests/GridOptimization.ipynb:147, nmslib brute_force, 4 threads, 3814^2 (other hardware)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc, self.thread = gpu_index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=5)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def build_workload(use_gpu_scan: bool):
+    """-> (guides u64[Q] in reference row order, uniq u64[N_u] in first-occurrence order, info)"""
+    from guidemaker_b200.synth import CONFIGS, config_genome
+    total, records, gc, seed = CONFIGS[WORKLOAD]
+    t0 = time.perf_counter()
+    recs = config_genome(WORKLOAD)
+    t_gen = time.perf_counter() - t0
+    buf = b"N".join(r.seq.encode() for r in recs)
+    if use_gpu_scan:
+        from guidemaker_b200 import _capi
+        g, _, _, nf, nr = _capi.pam_scan(buf, "NGG", False, GUIDE_LEN)
+        first = _capi.first_occurrence(g)
+    else:
+        from oracle import oracle as O
+        g, _, _, nf, nr = O.c_pam_scan(buf, "NGG", False, GUIDE_LEN)
+        first = O.c_first_occurrence(g)
+    uniq = np.ascontiguousarray(g[first == np.arange(len(g))])
+    info = {"workload": WORKLOAD, "genome_bases": total, "records": records, "gc": gc, "genome_seed": seed,
+            "pam": "NGG", "pam_orientation": "3prime", "guide_len": GUIDE_LEN, "metric_space": "hamming", "k": K_NEIGHBORS,
+            "queries": int(len(g)), "indexed_guides": int(len(uniq)), "comparisons_per_step": float(len(g)) * float(len(uniq)),
+            "genome_gen_s": round(t_gen, 3)}
+    return recs, g, uniq, info
+
+
+def cpu_bruteforce_rate(uniq, queries, seconds_target: float):
+    """exact CPU brute force (oracle port, all cores) on a bounded sample: ~seconds_target of work"""
+    from oracle import oracle as O
+    cores = O.num_threads()
+    probe = queries[: min(256, len(queries))]
+    t0 = time.perf_counter()
+    O.c_knn(uniq, probe, GUIDE_LEN, 0, K_NEIGHBORS)
+    rate = len(probe) * len(uniq) / (time.perf_counter() - t0)
+    n = int(min(len(queries), max(256, seconds_target * rate / len(uniq))))
+    rng = np.random.default_rng(0)
+    rows = np.sort(rng.choice(len(queries), size=n, replace=False))
+    sample = np.ascontiguousarray(queries[rows])
+    t0 = time.perf_counter()
+    O.c_knn(uniq, sample, GUIDE_LEN, 0, K_NEIGHBORS)
+    dt = time.perf_counter() - t0
+    return {"value": n * len(uniq) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d of %d query rows (seeded random subset) x all %d indexed guides, %.1f s, oracle/gm_oracle.c gmo_knn (OpenMP)"
+                      % (n, len(queries), len(uniq), dt)}, n, dt
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm.  Rank 0 only; other ranks exit without work."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    _, g, uniq, info = build_workload(use_gpu_scan=False)
+    per_step_s = 6.0
+    times, ns = [], []
+    for i in range(args.warmup + args.steps):
+        cb, n, dt = cpu_bruteforce_rate(uniq, g, per_step_s)
+        if i >= args.warmup:
+            times.append(dt); ns.append(n)
+    value = sum(ns) * float(len(uniq)) / sum(times)
+    cb["value"] = value
+    cb["sample"] = "each step: %d of %d query rows x all %d indexed guides (bounded sample of the workload)" % (ns[-1], len(g), len(uniq))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": info, "cpu_baseline": cb,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference engine nmslib==2.1.1 (HNSW) is not installable here; this arm times the exact CPU brute force "
+                    "it approximates (oracle port) on all host cores. Reference's own published brute_force figure: %.3g comparisons/s "
+                    "(4 threads, Carsonella 3814^2, unspecified laptop)" % PUBLISHED_REF_BRUTEFORCE}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from guidemaker_b200 import _capi
+    from guidemaker_b200.sharding import shard_bounds
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this benchmark has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    _capi.init(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    recs, g, uniq, info = build_workload(use_gpu_scan=True)
+    Q, NU, k = len(g), len(uniq), K_NEIGHBORS
+    lo, hi = shard_bounds(Q, rank, world)
+    rows_max = max(shard_bounds(Q, r, world)[1] - shard_bounds(Q, r, world)[0] for r in range(world))
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- device-resident state ------------------------------------------------------------------
+    d_uniq = torch.from_numpy(uniq.view(np.int64)).to(dev)
+    d_q = torch.from_numpy(np.ascontiguousarray(g[lo:hi]).view(np.int64)).to(dev)
+    ix = _capi.Index(None, GUIDE_LEN, 0, device_ptr=d_uniq.data_ptr(), n=NU, stream=stream)
+    d_idx = torch.full((rows_max, k), -1, dtype=torch.int32, device=dev)
+    d_dist = torch.full((rows_max, k), 255, dtype=torch.uint8, device=dev)
+    if world > 1:
+        g_idx = torch.empty((world * rows_max, k), dtype=torch.int32, device=dev)
+        g_dist = torch.empty((world * rows_max, k), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step_resident():
+        flush.zero_()                                                   # L2 flush between iterations
+        ix.knn_dev(d_q.data_ptr(), hi - lo, k, d_idx.data_ptr(), d_dist.data_ptr(), stream)
+        if world > 1:
+            dist.all_gather_into_tensor(g_idx, d_idx)
+            dist.all_gather_into_tensor(g_dist, d_dist)
+
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+
+    # ---- timed region: `value` ----------------------------------------------------------------------
+    _capi.prof_enable(True)
+    _capi.prof_reset()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    torch.cuda.synchronize(); barrier()
+    clocks = sampler.stop()
+    ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_total = float(ms_total.item())
+    prof = _capi.prof_read()
+    _capi.prof_enable(False)
+    comparisons = float(Q) * float(NU)
+    value = comparisons * args.steps / (ms_total * 1e-3)
+    launches_per_step = prof["all_kernel_launches"] / args.steps
+
+    # ---- result check (outside the timed region): rank 0 verifies a sample against the CPU oracle ------
+    checked = None
+    if rank == 0:
+        from oracle import oracle as O
+        full_idx = (g_idx if world > 1 else d_idx).cpu().numpy()
+        full_dist = (g_dist if world > 1 else d_dist).cpu().numpy()
+        if world > 1:
+            parts_i, parts_d = [], []
+            for r in range(world):
+                a, b = shard_bounds(Q, r, world)
+                parts_i.append(full_idx[r * rows_max: r * rows_max + (b - a)]); parts_d.append(full_dist[r * rows_max: r * rows_max + (b - a)])
+            full_idx, full_dist = np.concatenate(parts_i), np.concatenate(parts_d)
+        rows = np.random.default_rng(1).integers(0, Q, size=256)
+        oi, od = O.c_knn(uniq, g[rows], GUIDE_LEN, 0, k)
+        checked = bool(np.array_equal(full_idx[rows], oi) and np.array_equal(full_dist[rows], od))
+        if not checked:
+            raise SystemExit("bench.py: GPU result differs from the CPU oracle -- refusing to report a number")
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------------
+    popc_rate = _capi.microbench(0)                                  # lane-POPC/s of this GPU, measured now
+    scan_ms = prof["scan_kernel_ms"] / max(prof["scan_kernel_launches"], 1)
+    pairs_per_launch = prof["pairs"] / max(prof["scan_kernel_launches"], 1)
+    achieved = pairs_per_launch / (scan_ms * 1e-3)
+    roofline = {"bound": "int (XU pipe: 1 POPC per comparison; not hbm/tensor)", "achieved": achieved / 1e9, "peak": popc_rate / 1e9,
+                "unit": "Gcomparisons/s", "frac": achieved / popc_rate,
+                "peak_source": "measured live: gm_microbench(POPC), register-resident, whole GPU (16 POPC/clk/SM x 148 SM x SM clock)",
+                "kernel": "knn_hamming_scan_kernel<R>", "kernel_ms_per_launch": scan_ms,
+                "kernel_share_of_step": prof["scan_kernel_ms"] / ms_total,
+                "algorithmic_bytes_per_launch": float(NU) * 8 + float(hi - lo) * (8 + 5 * k),
+                "hbm_equiv_gbs": (float(NU) * 8 + float(hi - lo) * (8 + 5 * k)) / (scan_ms * 1e-3) / 1e9,
+                "traffic": None}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get("knn_hamming_scan_kernel_dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ---------------------------
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()          # noqa: E731
+    h_uniq = pin(uniq.view(np.int64)).view(np.uint64)
+    h_q = pin(np.ascontiguousarray(g[lo:hi]).view(np.int64)).view(np.uint64)
+    h_idx = pin(np.empty((hi - lo, k), np.int32)); h_dist = pin(np.empty((hi - lo, k), np.uint8))
+
+    def step_e2e():
+        hix = _capi.Index(h_uniq, GUIDE_LEN, 0)                        # H2D guide table
+        hix.knn(h_q, k, out_idx=h_idx, out_dist=h_dist)                # H2D queries, kernels, D2H results
+        hix.close()
+        if world > 1:                                                  # every rank ends up with the full table
+            ti = torch.from_numpy(h_idx).to(dev, non_blocking=True); td = torch.from_numpy(h_dist).to(dev, non_blocking=True)
+            pi = torch.full((rows_max, k), -1, dtype=torch.int32, device=dev); pd_ = torch.full((rows_max, k), 255, dtype=torch.uint8, device=dev)
+            pi[: hi - lo] = ti; pd_[: hi - lo] = td
+            dist.all_gather_into_tensor(g_idx, pi); dist.all_gather_into_tensor(g_dist, pd_)
+            g_idx.cpu(); g_dist.cpu()
+
+    e2e_steps = max(2, min(args.steps, 5))
+    step_e2e()
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize(); barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e = {"value": comparisons * e2e_steps / float(dt.item()), "unit": UNIT,
+           "h2d_bytes_per_step": int(NU * 8 + (hi - lo) * 8), "d2h_bytes_per_step": int((hi - lo) * k * 5),
+           "steps": e2e_steps, "api": "ctypes: gm_index_create + gm_knn + gm_index_free (host buffers, pinned)"}
+
+    # ---- genome wall time through the public Python API (find_targets -> get_neighbors) ----------------
+    wall = None
+    if rank == 0 or world > 1:
+        import tempfile
+        import yaml
+        import guidemaker_b200 as gmk
+        cfg = tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False)
+        yaml.safe_dump({"NMSLIB": {"M": 16, "efc": 10, "post": 1, "ef": 9},
+                        "CONTROL": {"MINIMUM_HMDIST": 7, "CONTROL_SEARCH_MULTIPLE": [10, 100, 1000, 10000]}}, cfg)
+        cfg.close()
+        t = [time.perf_counter()]
+        df = gmk.PamTarget("NGG", "3prime", "hamming").find_targets(recs, GUIDE_LEN); t.append(time.perf_counter())
+        tp = gmk.TargetProcessor(df, lsr=10, editdist=2, knum=k)
+        tp.check_restriction_enzymes([]); tp.find_unique_near_pam(); t.append(time.perf_counter())
+        tp.create_index(cfg.name); t.append(time.perf_counter())
+        tp.get_neighbors(cfg.name); t.append(time.perf_counter())
+        os.unlink(cfg.name)
+        wall = {"total_s": round(t[-1] - t[0], 3), "find_targets_s": round(t[1] - t[0], 3), "find_unique_near_pam_s": round(t[2] - t[1], 3),
+                "create_index_s": round(t[3] - t[2], 3), "get_neighbors_s": round(t[4] - t[3], 3),
+                "guides_kept": len(tp.neighbors), "api": "guidemaker_b200.PamTarget/TargetProcessor (pandas in/out)"}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1:
+        cpu, _, _ = cpu_bruteforce_rate(uniq, g, 12.0)
+
+    if rank == 0:
+        info.update({"parallelism": "query rows sharded x%d, guide table replicated, NCCL all-gather of top-k" % world if world > 1 else "single GPU",
+                     "l2": "256 MiB buffer rewritten between timed iterations (L2 flush)", "queries_per_rank": rows_max})
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u32", "data": "synthetic", "config": info, "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(prof["all_kernel_launches"]), "gpu_launches_per_step": launches_per_step,
+                "roofline": roofline, "cpu_baseline": cpu, "genome_wall": wall, "oracle_check_256_rows": checked,
+                "published_reference_bruteforce_cps": PUBLISHED_REF_BRUTEFORCE}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -164,10 +164,14 @@ class Index:
             self.n = int(n)
             _check(lib.gm_index_create_dev(_vp(device_ptr), self.n, self.L, self.metric, ctypes.byref(self._h), _vp(stream)), "gm_index_create_dev")
 
-    def knn(self, q2bit: np.ndarray, k: int):
+    def knn(self, q2bit: np.ndarray, k: int, out_idx: np.ndarray | None = None, out_dist: np.ndarray | None = None):
+        """host buffers in, host buffers out (synchronous); out_* may be caller-owned (e.g. pinned) arrays"""
         q2bit = np.ascontiguousarray(q2bit, np.uint64)
         q = len(q2bit)
-        idx = np.empty((q, k), np.int32); dist = np.empty((q, k), np.uint8)
+        idx = np.empty((q, k), np.int32) if out_idx is None else out_idx
+        dist = np.empty((q, k), np.uint8) if out_dist is None else out_dist
+        assert idx.shape == (q, k) and idx.dtype == np.int32 and idx.flags.c_contiguous
+        assert dist.shape == (q, k) and dist.dtype == np.uint8 and dist.flags.c_contiguous
         _check(load_library().gm_knn(self._h, _p(q2bit) if q else None, q, int(k), _p(idx), _p(dist)), "gm_knn")
         return idx, dist
 

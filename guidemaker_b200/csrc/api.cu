@@ -1,6 +1,8 @@
 // api.cu -- library lifecycle, error reporting, profiling hooks and the register-resident
 // instruction-rate microbenchmarks that serve as roofline denominators for the INT pipes.
 #include <stdarg.h>
+#include <stdlib.h>
+#include <chrono>
 
 #include "common.cuh"
 
@@ -27,6 +29,18 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
 }
 
 Prof &prof() { return g_prof; }
+
+bool trace_on() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("GM_TRACE"); on = (e && e[0] == '1') ? 1 : 0; }
+    return on == 1;
+}
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+void trace(const char *what, double t0_ms) {
+    if (trace_on()) fprintf(stderr, "[gm_trace] %-28s %9.3f ms\n", what, now_ms() - t0_ms);
+}
 int device_sm_count() { return g_sm_count; }
 bool initialised() { return g_device >= 0; }
 
@@ -65,6 +79,12 @@ extern "C" int gm_init(int device) {
     }
     GM_CUDA(cudaSetDevice(device));
     GM_CUDA(cudaFree(0));
+    {   // keep freed blocks in the stream-ordered pool (no unmap between calls)
+        cudaMemPool_t pool;
+        GM_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ULL;
+        GM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     g_device = device;
     g_sm_count = p.multiProcessorCount;
     g_cc_major = p.major;
@@ -183,8 +203,8 @@ extern "C" int gm_microbench(int what, double *ops_per_s) {
     if (rc) return rc;
     GM_ARG(what >= 0 && what <= 2 && ops_per_s, "gm_microbench: what must be 0..2");
     uint32_t *d = nullptr;
-    GM_CUDA(cudaMalloc(&d, 64));
-    GM_CUDA(cudaMemset(d, 0, 64));
+    GM_CUDA(dev_alloc((void **)&d, 64, 0));
+    GM_CUDA(cudaMemsetAsync(d, 0, 64, 0));
     const int grid = g_sm_count * 8, iters = 8192;
     cudaEvent_t e0, e1;
     GM_CUDA(cudaEventCreate(&e0));
@@ -205,7 +225,7 @@ extern "C" int gm_microbench(int what, double *ops_per_s) {
     GM_CUDA(cudaGetLastError());
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    cudaFree(d);
+    dev_free(d, 0);
     *ops_per_s = (double)grid * 256.0 * iters * MB_CHAINS / (best * 1e-3);
     return GM_OK;
 }

@@ -42,6 +42,16 @@ int device_sm_count();
 bool initialised();
 int ensure_init();
 
+// Device memory comes from the stream-ordered allocator; gm_init raises the pool's release threshold
+// so freed blocks stay mapped and the next call's allocations cost microseconds, not a map/unmap.
+inline cudaError_t dev_alloc(void **p, size_t bytes, cudaStream_t st) { return cudaMallocAsync(p, bytes ? bytes : 16, st); }
+inline void dev_free(void *p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
+
+// GM_TRACE=1 prints wall-clock per host-side phase of the host-buffer entry points
+bool trace_on();
+double now_ms();
+void trace(const char *what, double t0_ms);
+
 // ---- device helpers ---------------------------------------------------------------------------------
 #ifdef __CUDACC__
 

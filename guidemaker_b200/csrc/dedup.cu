@@ -73,11 +73,11 @@ static int dedup_run(const uint64_t *h_keys, int64_t n, int L, int lsr, int five
     unsigned int *d_minrow = nullptr;
     uint8_t *d_dup = nullptr;
     int64_t *d_first = nullptr;
-    cudaError_t e = cudaMalloc(&d_keys, (size_t)n * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&d_slots, cap * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&d_minrow, cap * 4);
-    if (e == cudaSuccess && h_is_dup) e = cudaMalloc(&d_dup, (size_t)n);
-    if (e == cudaSuccess && h_first_row) e = cudaMalloc(&d_first, (size_t)n * 8);
+    cudaError_t e = dev_alloc((void **)&d_keys, (size_t)n * 8, 0);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_slots, cap * 8, 0);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_minrow, cap * 4, 0);
+    if (e == cudaSuccess && h_is_dup) e = dev_alloc((void **)&d_dup, (size_t)n, 0);
+    if (e == cudaSuccess && h_first_row) e = dev_alloc((void **)&d_first, (size_t)n * 8, 0);
     if (e == cudaSuccess) e = cudaMemcpy(d_keys, h_keys, (size_t)n * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(d_slots, 0xFF, cap * 8);
     if (e == cudaSuccess) e = cudaMemset(d_minrow, 0xFF, cap * 4);
@@ -91,7 +91,7 @@ static int dedup_run(const uint64_t *h_keys, int64_t n, int L, int lsr, int five
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess && h_is_dup) e = cudaMemcpy(h_is_dup, d_dup, (size_t)n, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && h_first_row) e = cudaMemcpy(h_first_row, d_first, (size_t)n * 8, cudaMemcpyDeviceToHost);
-    cudaFree(d_keys); cudaFree(d_slots); cudaFree(d_minrow); cudaFree(d_dup); cudaFree(d_first);
+    dev_free(d_keys, 0); dev_free(d_slots, 0); dev_free(d_minrow, 0); dev_free(d_dup, 0); dev_free(d_first, 0);
     if (e != cudaSuccess) return cuda_fail(e, "dedup", __FILE__, __LINE__);
     return GM_OK;
 }

@@ -309,16 +309,13 @@ __global__ void knn_merge_kernel(const uint32_t *__restrict__ lists, int splits,
 
 // ---- host side ------------------------------------------------------------------------------------------
 
-static int ensure_ws(Index *ix, size_t bytes) {
+static int ensure_ws(Index *ix, size_t bytes, cudaStream_t st) {
     if (bytes <= ix->ws_bytes) return GM_OK;
-    if (ix->ws) {
-        GM_CUDA(cudaDeviceSynchronize());
-        GM_CUDA(cudaFree(ix->ws));
-        ix->ws = nullptr;
-        ix->ws_bytes = 0;
-    }
+    dev_free(ix->ws, st);                      // stream ordered: earlier kernels on `st` finish first
+    ix->ws = nullptr;
+    ix->ws_bytes = 0;
     bytes = (bytes + (bytes >> 3) + 4095) & ~(size_t)4095;
-    GM_CUDA(cudaMalloc(&ix->ws, bytes));
+    GM_CUDA(dev_alloc(&ix->ws, bytes, st));
     ix->ws_bytes = bytes;
     return GM_OK;
 }
@@ -365,7 +362,7 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     const size_t qp_bytes = (size_t)q_pad * sizeof(uint2);
     const size_t list_bytes = (size_t)splits * q_pad * k * sizeof(uint32_t);
     const size_t warm_bytes = warm ? (size_t)q_pad * k * sizeof(uint32_t) : 0;
-    int rc = ensure_ws(ix, qp_bytes + list_bytes + warm_bytes);
+    int rc = ensure_ws(ix, qp_bytes + list_bytes + warm_bytes, st);
     if (rc) return rc;
     uint2 *qplanes = reinterpret_cast<uint2 *>(ix->ws);
     uint32_t *lists = reinterpret_cast<uint32_t *>((char *)ix->ws + qp_bytes);
@@ -441,13 +438,13 @@ extern "C" int gm_index_create_dev(const uint64_t *d_uniq2bit, int64_t n_u, int 
     ix->n_pad = (n_u + CHUNK - 1) / CHUNK * CHUNK;
     ix->L = L;
     ix->metric = metric;
-    cudaError_t e = cudaMalloc(&ix->planes, (size_t)ix->n_pad * sizeof(uint2));
-    if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaMalloc(index)", __FILE__, __LINE__); }
     cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = dev_alloc((void **)&ix->planes, (size_t)ix->n_pad * sizeof(uint2), st);
+    if (e != cudaSuccess) { delete ix; return cuda_fail(e, "dev_alloc(index)", __FILE__, __LINE__); }
     to_planes_kernel<<<(unsigned)((ix->n_pad + 255) / 256), 256, 0, st>>>(d_uniq2bit, n_u, ix->n_pad, ix->planes);
     count_launch();
     e = cudaGetLastError();
-    if (e != cudaSuccess) { cudaFree(ix->planes); delete ix; return cuda_fail(e, "to_planes_kernel", __FILE__, __LINE__); }
+    if (e != cudaSuccess) { dev_free(ix->planes, st); delete ix; return cuda_fail(e, "to_planes_kernel", __FILE__, __LINE__); }
     *index = ix;
     return GM_OK;
 }
@@ -459,12 +456,14 @@ extern "C" int gm_index_create(const uint64_t *uniq2bit, int64_t n_u, int L, int
     *index = nullptr;
     GM_ARG(uniq2bit && n_u >= 1, "gm_index_create: empty guide table");
     uint64_t *d = nullptr;
-    GM_CUDA(cudaMalloc(&d, (size_t)n_u * sizeof(uint64_t)));
-    cudaError_t e = cudaMemcpy(d, uniq2bit, (size_t)n_u * sizeof(uint64_t), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "cudaMemcpy(H2D guides)", __FILE__, __LINE__); }
+    const double t0 = now_ms();
+    GM_CUDA(dev_alloc((void **)&d, (size_t)n_u * sizeof(uint64_t), 0));
+    cudaError_t e = cudaMemcpyAsync(d, uniq2bit, (size_t)n_u * sizeof(uint64_t), cudaMemcpyHostToDevice, 0);
+    if (e != cudaSuccess) { dev_free(d, 0); return cuda_fail(e, "cudaMemcpy(H2D guides)", __FILE__, __LINE__); }
     rc = gm_index_create_dev(d, n_u, L, metric, index, nullptr);
-    cudaError_t e2 = cudaDeviceSynchronize();
-    cudaFree(d);
+    dev_free(d, 0);
+    cudaError_t e2 = cudaStreamSynchronize(0);
+    trace("gm_index_create", t0);
     if (rc) return rc;
     if (e2 != cudaSuccess) { gm_index_free(*index); *index = nullptr; return cuda_fail(e2, "index build", __FILE__, __LINE__); }
     return GM_OK;
@@ -483,8 +482,8 @@ extern "C" int gm_index_free(void *index) {
     Index *ix = (Index *)index;
     if (!ix) return GM_OK;
     cudaDeviceSynchronize();
-    if (ix->planes) cudaFree(ix->planes);
-    if (ix->ws) cudaFree(ix->ws);
+    dev_free(ix->planes, 0);
+    dev_free(ix->ws, 0);
     delete ix;
     return GM_OK;
 }
@@ -514,21 +513,28 @@ static int knn_host(void *index, const uint64_t *q2bit, int64_t q, int k, int32_
     int32_t *d_idx = nullptr;
     uint8_t *d_dist = nullptr;
     const size_t nd = dist_only ? (size_t)q : (size_t)q * k;
-    cudaError_t e = cudaMalloc(&d_q, (size_t)q * sizeof(uint64_t));
-    if (e == cudaSuccess && !dist_only) e = cudaMalloc(&d_idx, nd * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&d_dist, nd);
-    if (e == cudaSuccess) e = cudaMemcpy(d_q, q2bit, (size_t)q * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    cudaStream_t st = 0;
+    double t0 = now_ms();
+    cudaError_t e = dev_alloc((void **)&d_q, (size_t)q * sizeof(uint64_t), st);
+    if (e == cudaSuccess && !dist_only) e = dev_alloc((void **)&d_idx, nd * sizeof(int32_t), st);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_dist, nd, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_q, q2bit, (size_t)q * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
+    trace("knn: alloc + H2D enqueue", t0);
     if (e == cudaSuccess) {
-        rc = knn_run((Index *)index, d_q, q, k, d_idx, d_dist, dist_only, nullptr);
+        t0 = now_ms();
+        rc = knn_run((Index *)index, d_q, q, k, d_idx, d_dist, dist_only, st);
+        trace("knn: launch", t0);
         if (rc == GM_OK) {
-            e = cudaDeviceSynchronize();
-            if (e == cudaSuccess && !dist_only) e = cudaMemcpy(out_idx, d_idx, nd * sizeof(int32_t), cudaMemcpyDeviceToHost);
-            if (e == cudaSuccess) e = cudaMemcpy(out_dist, d_dist, nd, cudaMemcpyDeviceToHost);
+            t0 = now_ms();
+            if (!dist_only) e = cudaMemcpyAsync(out_idx, d_idx, nd * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out_dist, d_dist, nd, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            trace("knn: kernels + D2H", t0);
         }
     }
-    cudaFree(d_q);
-    cudaFree(d_idx);
-    cudaFree(d_dist);
+    dev_free(d_q, st);
+    dev_free(d_idx, st);
+    dev_free(d_dist, st);
     if (rc) return rc;
     if (e != cudaSuccess) return cuda_fail(e, "gm_knn", __FILE__, __LINE__);
     return GM_OK;

@@ -261,9 +261,9 @@ using namespace gm;
 extern "C" int gm_scan_free(void *scan) {
     Scan *s = (Scan *)scan;
     if (!s) return GM_OK;
-    cudaFree(s->guides);
-    cudaFree(s->start);
-    cudaFree(s->pamcode);
+    dev_free(s->guides, 0);
+    dev_free(s->start, 0);
+    dev_free(s->pamcode, 0);
     delete s;
     return GM_OK;
 }
@@ -306,10 +306,10 @@ extern "C" int gm_scan_create(const uint8_t *seq_ascii, int64_t n, const char *p
     uint32_t *d_planes = nullptr, *d_blk = nullptr;
     uint64_t *d_off = nullptr;
     uint64_t totals[2] = {0, 0};
-    cudaError_t e = cudaMalloc(&d_seq, (size_t)n_words * 32);
-    if (e == cudaSuccess) e = cudaMalloc(&d_planes, 3 * plane_words * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&d_blk, (size_t)n_blocks * 2 * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&d_off, ((size_t)n_blocks * 2 + 2) * 8);
+    cudaError_t e = dev_alloc((void **)&d_seq, (size_t)n_words * 32, 0);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_planes, 3 * plane_words * 4, 0);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_blk, (size_t)n_blocks * 2 * 4, 0);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_off, ((size_t)n_blocks * 2 + 2) * 8, 0);
     if (e == cudaSuccess) e = cudaMemset(d_seq + (n_words - 1) * 32, 0, 32);
     if (e == cudaSuccess) e = cudaMemcpy(d_seq, seq_ascii, (size_t)n, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(d_planes, 0, 3 * plane_words * 4);
@@ -326,9 +326,9 @@ extern "C" int gm_scan_create(const uint8_t *seq_ascii, int64_t n, const char *p
     if (e == cudaSuccess) e = cudaMemcpy(totals, d_tot, sizeof totals, cudaMemcpyDeviceToHost);
     const int64_t nf = (int64_t)totals[0], nr = (int64_t)totals[1], nt = nf + nr;
     if (e == cudaSuccess && nt > 0) {
-        e = cudaMalloc(&s->guides, (size_t)nt * 8);
-        if (e == cudaSuccess) e = cudaMalloc(&s->start, (size_t)nt * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&s->pamcode, (size_t)nt * 2);
+        e = dev_alloc((void **)&s->guides, (size_t)nt * 8, 0);
+        if (e == cudaSuccess) e = dev_alloc((void **)&s->start, (size_t)nt * 4, 0);
+        if (e == cudaSuccess) e = dev_alloc((void **)&s->pamcode, (size_t)nt * 2, 0);
         if (e == cudaSuccess) {
             scan_emit_kernel<<<(unsigned)n_blocks, SCAN_THREADS>>>(pp, n_words, lo, hi, va, off_f, off_r, (uint64_t)nf,
                                                                    s->guides, s->start, s->pamcode);
@@ -337,10 +337,10 @@ extern "C" int gm_scan_create(const uint8_t *seq_ascii, int64_t n, const char *p
         }
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
     }
-    cudaFree(d_seq);
-    cudaFree(d_planes);
-    cudaFree(d_blk);
-    cudaFree(d_off);
+    dev_free(d_seq, 0);
+    dev_free(d_planes, 0);
+    dev_free(d_blk, 0);
+    dev_free(d_off, 0);
     if (e != cudaSuccess) {
         gm_scan_free(s);
         *scan = nullptr;
