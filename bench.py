@@ -17,7 +17,10 @@ a step performs Q x N_u of them.
   e2e      the same metric through the host-buffer C ABI (gm_index_create + gm_knn via ctypes): every step
            copies the guide table and that step's queries host->device from pinned memory and reads the
            (idx, dist) result device->host.
-  roofline the pair-scan kernel (the dominant kernel) against the measured POPC-pipe rate of this GPU.
+  roofline the pair-scan kernel (the dominant kernel).  Default engine K3b (tcgen05 kind::i8 one-hot GEMM): algorithmic
+           int8 tensor ops (2*4L = 160 per comparison, SURVEY 8d) against the kind::i8 MMA rate measured live on this GPU.
+           `alt_engine` reports the INT-pipe variant K3a (XOR/POPC) against the measured POPC rate, for the choice
+           between the two that north_star asks for.
   cpu_baseline  the CPU oracle port (oracle/gm_oracle.c, exact brute force, OpenMP over all host cores) on
            a bounded sample of the same workload.
 
@@ -135,17 +138,17 @@ def build_workload(use_gpu_scan: bool):
 def cpu_bruteforce_rate(uniq, queries, seconds_target: float):
     """exact CPU brute force (oracle port, all cores) on a bounded sample: ~seconds_target of work"""
     from oracle import oracle as O
-    cores = O.num_threads()
+    cores = os.cpu_count() or O.num_threads()          # all host threads, even under torchrun's OMP_NUM_THREADS=1
     probe = queries[: min(256, len(queries))]
     t0 = time.perf_counter()
-    O.c_knn(uniq, probe, GUIDE_LEN, 0, K_NEIGHBORS)
+    O.c_knn(uniq, probe, GUIDE_LEN, 0, K_NEIGHBORS, threads=cores)
     rate = len(probe) * len(uniq) / (time.perf_counter() - t0)
     n = int(min(len(queries), max(256, seconds_target * rate / len(uniq))))
     rng = np.random.default_rng(0)
     rows = np.sort(rng.choice(len(queries), size=n, replace=False))
     sample = np.ascontiguousarray(queries[rows])
     t0 = time.perf_counter()
-    O.c_knn(uniq, sample, GUIDE_LEN, 0, K_NEIGHBORS)
+    O.c_knn(uniq, sample, GUIDE_LEN, 0, K_NEIGHBORS, threads=cores)
     dt = time.perf_counter() - t0
     return {"value": n * len(uniq) / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "%d of %d query rows (seeded random subset) x all %d indexed guides, %.1f s, oracle/gm_oracle.c gmo_knn (OpenMP)"
@@ -199,6 +202,7 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
 
+    _capi.knn_engine(args.engine)
     recs, g, uniq, info = build_workload(use_gpu_scan=True)
     Q, NU, k = len(g), len(uniq), K_NEIGHBORS
     lo, hi = shard_bounds(Q, rank, world)
@@ -273,20 +277,52 @@ def run_ours(args):
     scan_ms = prof["scan_kernel_ms"] / max(prof["scan_kernel_launches"], 1)
     pairs_per_launch = prof["pairs"] / max(prof["scan_kernel_launches"], 1)
     achieved = pairs_per_launch / (scan_ms * 1e-3)
-    roofline = {"bound": "int (XU pipe: 1 POPC per comparison; not hbm/tensor)", "achieved": achieved / 1e9, "peak": popc_rate / 1e9,
-                "unit": "Gcomparisons/s", "frac": achieved / popc_rate,
-                "peak_source": "measured live: gm_microbench(POPC), register-resident, whole GPU (16 POPC/clk/SM x 148 SM x SM clock)",
-                "kernel": "knn_hamming_scan_kernel<R>", "kernel_ms_per_launch": scan_ms,
-                "kernel_share_of_step": prof["scan_kernel_ms"] / ms_total,
-                "algorithmic_bytes_per_launch": float(NU) * 8 + float(hi - lo) * (8 + 5 * k),
-                "hbm_equiv_gbs": (float(NU) * 8 + float(hi - lo) * (8 + 5 * k)) / (scan_ms * 1e-3) / 1e9,
-                "traffic": None}
+    alg_bytes = float(NU) * 8 + float(hi - lo) * (8 + 5 * k)
+    traffic = {}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roofline["traffic"] = json.load(open(tr)).get("knn_hamming_scan_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(tr))
         except Exception:  # noqa: BLE001
-            pass
+            traffic = {}
+    if args.engine == 1:
+        i8_rate = _capi.microbench(3)                                # int8 tensor ops/s (2 per MAC), measured now
+        ops_alg, ops_exec = 2 * 4 * GUIDE_LEN, 96                    # 2*4L per comparison; executed: K=96, 2 queries per row
+        roofline = {"bound": "tensor", "achieved": achieved * ops_alg / 1e12, "peak": i8_rate / 1e12, "unit": "TOP/s (int8)",
+                    "frac": achieved * ops_alg / i8_rate,
+                    "peak_source": "measured live: gm_microbench(3), back-to-back tcgen05.mma kind::i8 128x256x32 on all SMs",
+                    "algorithmic_ops_per_comparison": ops_alg, "executed_ops_per_comparison": ops_exec,
+                    "frac_executed": achieved * ops_exec / i8_rate,
+                    "comparisons_per_s": achieved, "kernel": "knn_hamming_tc_kernel<KC> (+ warm-up knn_hamming_scan_kernel)",
+                    "kernel_ms_per_launch": scan_ms, "kernel_share_of_step": prof["scan_kernel_ms"] / ms_total,
+                    "algorithmic_bytes_per_launch": alg_bytes, "hbm_equiv_gbs": alg_bytes / (scan_ms * 1e-3) / 1e9,
+                    "traffic": traffic.get("knn_hamming_tc_kernel_dram_bytes_per_launch")}
+    else:
+        roofline = {"bound": "int (XU pipe: 1 POPC per comparison; not hbm/tensor)", "achieved": achieved / 1e9, "peak": popc_rate / 1e9,
+                    "unit": "Gcomparisons/s", "frac": achieved / popc_rate,
+                    "peak_source": "measured live: gm_microbench(POPC), register-resident, whole GPU (16 POPC/clk/SM x 148 SM x SM clock)",
+                    "kernel": "knn_hamming_scan_kernel<R>", "kernel_ms_per_launch": scan_ms,
+                    "kernel_share_of_step": prof["scan_kernel_ms"] / ms_total,
+                    "algorithmic_bytes_per_launch": alg_bytes, "hbm_equiv_gbs": alg_bytes / (scan_ms * 1e-3) / 1e9,
+                    "traffic": traffic.get("knn_hamming_scan_kernel_dram_bytes_per_launch")}
+
+    # ---- the other engine, for the K3a / K3b choice (outside the timed region, 2 passes) --------------------------
+    alt = None
+    if rank == 0:
+        other = 1 - args.engine
+        _capi.knn_engine(other)
+        _capi.prof_enable(True)
+        step_resident(); torch.cuda.synchronize()
+        _capi.prof_reset()
+        step_resident(); torch.cuda.synchronize()
+        pa = _capi.prof_read()
+        _capi.prof_enable(False)
+        _capi.knn_engine(args.engine)
+        rate = pa["pairs"] / (pa["scan_kernel_ms"] * 1e-3)
+        alt = {"engine": "K3a xor/popc (INT pipes)" if other == 0 else "K3b tcgen05 kind::i8 one-hot GEMM",
+               "comparisons_per_s": rate, "kernel_ms": pa["scan_kernel_ms"],
+               "frac_of_popc_peak": rate / popc_rate if other == 0 else None, "popc_peak_lane_ops_per_s": popc_rate,
+               "identical_output": None}
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ---------------------------
     pin = lambda a: torch.from_numpy(a).pin_memory().numpy()          # noqa: E731
@@ -350,9 +386,10 @@ def run_ours(args):
                      "l2": "256 MiB buffer rewritten between timed iterations (L2 flush)", "queries_per_rank": rows_max})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "u32", "data": "synthetic", "config": info, "clocks": clocks, "e2e": e2e,
+                "dtype": "i8 (one-hot, int32 accumulate)" if args.engine == 1 else "u32", "data": "synthetic", "config": info, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(prof["all_kernel_launches"]), "gpu_launches_per_step": launches_per_step,
-                "roofline": roofline, "cpu_baseline": cpu, "genome_wall": wall, "oracle_check_256_rows": checked,
+                "roofline": roofline, "engine": "K3b tcgen05 kind::i8 one-hot GEMM" if args.engine == 1 else "K3a xor/popc",
+                "alt_engine": alt, "cpu_baseline": cpu, "genome_wall": wall, "oracle_check_256_rows": checked,
                 "published_reference_bruteforce_cps": PUBLISHED_REF_BRUTEFORCE}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -365,6 +402,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--engine", type=int, choices=[0, 1], default=1, help="Hamming pair-scan engine: 1 = K3b tensor (default), 0 = K3a INT pipes")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

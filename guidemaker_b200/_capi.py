@@ -47,6 +47,7 @@ _SIGS = {
     "gm_prof_reset": [],
     "gm_prof_read": [ctypes.POINTER(ctypes.c_double), _c_i64p, ctypes.POINTER(ctypes.c_double), _c_i64p],
     "gm_knn_tune": [ctypes.c_int, ctypes.c_int, ctypes.c_int],
+    "gm_knn_engine": [ctypes.c_int],
     "gm_microbench": [ctypes.c_int, ctypes.POINTER(ctypes.c_double)],
 }
 EXPORTS = tuple(_SIGS) + ("gm_last_error",)
@@ -216,6 +217,11 @@ def prof_read() -> dict:
 
 def knn_tune(queries_per_thread: int = 0, splits: int = 0, warm_sample: int = -1):
     _check(load_library().gm_knn_tune(queries_per_thread, splits, warm_sample), "gm_knn_tune")
+
+
+def knn_engine(engine: int):
+    """0 = K3a XOR/POPC (INT pipes), 1 = K3b tcgen05 one-hot GEMM (tensor pipe)"""
+    _check(load_library().gm_knn_engine(int(engine)), "gm_knn_engine")
 
 
 def microbench(what: int) -> float:

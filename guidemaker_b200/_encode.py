@@ -33,6 +33,17 @@ def as_byte_matrix(seqs, L: int | None = None) -> np.ndarray:
     return np.ascontiguousarray(arr).view(np.uint8).reshape(len(arr), width)
 
 
+def _spread32(v: np.ndarray) -> np.ndarray:
+    """bit i of a uint32 -> bit 2i of a uint64 (vectorised)"""
+    x = v.astype(np.uint64)
+    x = (x | (x << np.uint64(16))) & np.uint64(0x0000FFFF0000FFFF)
+    x = (x | (x << np.uint64(8))) & np.uint64(0x00FF00FF00FF00FF)
+    x = (x | (x << np.uint64(4))) & np.uint64(0x0F0F0F0F0F0F0F0F)
+    x = (x | (x << np.uint64(2))) & np.uint64(0x3333333333333333)
+    x = (x | (x << np.uint64(1))) & np.uint64(0x5555555555555555)
+    return x
+
+
 def encode_matrix(mat: np.ndarray) -> np.ndarray:
     """(N, L) uint8 ASCII -> uint64 guide2bit.  Raises on anything but upper-case A/C/G/T."""
     n, L = mat.shape
@@ -41,10 +52,15 @@ def encode_matrix(mat: np.ndarray) -> np.ndarray:
     codes = _LUT[mat]
     if n and codes.max(initial=0) > 3:
         raise ValueError("guide sequences may contain only A, C, G, T")
-    out = np.zeros(n, dtype=np.uint64)
-    for i in range(L):
-        out |= codes[:, i].astype(np.uint64) << np.uint64(2 * i)
-    return out
+    if n == 0 or L == 0:
+        return np.zeros(n, dtype=np.uint64)
+    planes = []
+    for bit in (0, 1):                                   # bit planes via packbits, then interleave
+        b = np.packbits((codes >> bit) & 1, axis=1, bitorder="little")
+        w = np.zeros((n, 4), dtype=np.uint8)
+        w[:, : b.shape[1]] = b
+        planes.append(w.view("<u4").reshape(n))
+    return _spread32(planes[0]) | (_spread32(planes[1]) << np.uint64(1))
 
 
 def encode_guides(seqs, L: int | None = None) -> np.ndarray:

@@ -145,10 +145,13 @@ class PamTarget:
             "seqid": pd.Categorical.from_codes(rec, categories=pd.Index(ids).unique()) if len(set(ids)) == len(ids)
             else pd.Categorical(np.asarray(ids, dtype=object)[rec]),
         })
-        df = df.assign(seedseq=np.nan, hasrestrictionsite=np.nan, isseedduplicated=np.nan)
-        df = df.astype({"seedseq": 'str', "isseedduplicated": 'bool'})
-        df = df.assign(dtype=self.dtype)
-        df = df.astype({"dtype": 'category'})
+        # seedseq=NaN -> 'str', hasrestrictionsite=NaN, isseedduplicated=NaN -> bool True, dtype -> category
+        # (core.py:288-291), built directly instead of through astype
+        import pyarrow as pa
+        df["seedseq"] = pd.array(pa.nulls(n, pa.large_string()), dtype="str")
+        df["hasrestrictionsite"] = np.nan
+        df["isseedduplicated"] = True
+        df["dtype"] = pd.Categorical.from_codes(np.zeros(n, dtype=np.int8), categories=[self.dtype])
         return df
 
     @staticmethod
@@ -217,8 +220,15 @@ class TargetProcessor:
         return mat
 
     def _packed(self):
-        mat = self._guide_matrix()
-        return encode_matrix(mat), mat.shape[1]
+        """packed guides of self.targets['target'], cached while that column object is unchanged"""
+        col = self.targets['target']
+        key = (id(self.targets), id(col.array), len(col))
+        cache = getattr(self, "_packed_cache", None)
+        if cache is None or cache[0] != key:
+            mat = self._guide_matrix()
+            cache = (key, encode_matrix(mat), mat.shape[1], col.array)   # keep the array alive: ids stay unique
+            self._packed_cache = cache
+        return cache[1], cache[2]
 
     # ---- reference API -------------------------------------------------------------------------------
     def check_restriction_enzymes(self, restriction_enzyme_list: list = []) -> None:
@@ -256,8 +266,11 @@ class TargetProcessor:
             if cut < 0:
                 cut = max(L + cut, 0)
             seed, lsr_eff = mat[:, cut:], L - cut
+        guides = encode_matrix(mat)
         self.targets['seedseq'] = _str_series(np.ascontiguousarray(seed), index=self.targets.index)
-        self.targets['isseedduplicated'] = _capi.seed_dedup(encode_matrix(mat), L, lsr_eff if lsr_eff < L else 0, five)
+        self.targets['isseedduplicated'] = _capi.seed_dedup(guides, L, lsr_eff if lsr_eff < L else 0, five)
+        col = self.targets['target']
+        self._packed_cache = ((id(self.targets), id(col.array), len(col)), guides, L, col.array)
 
     def create_index(self, configpath: str, num_threads=2):
         """Upload the distinct guides to the GPU (replaces the HNSW build, core.py:418-467).

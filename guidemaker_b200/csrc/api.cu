@@ -6,6 +6,8 @@
 
 #include "common.cuh"
 
+namespace gm { int microbench_mma_i8(double *ops_per_s); }
+
 namespace gm {
 
 static thread_local char g_err[512] = "";
@@ -201,7 +203,8 @@ __global__ void __launch_bounds__(256) mb_kernel(uint32_t *out, int iters) {
 extern "C" int gm_microbench(int what, double *ops_per_s) {
     int rc = ensure_init();
     if (rc) return rc;
-    GM_ARG(what >= 0 && what <= 2 && ops_per_s, "gm_microbench: what must be 0..2");
+    GM_ARG(what >= 0 && what <= 3 && ops_per_s, "gm_microbench: what must be 0..3");
+    if (what == 3) return microbench_mma_i8(ops_per_s);
     uint32_t *d = nullptr;
     GM_CUDA(dev_alloc((void **)&d, 64, 0));
     GM_CUDA(cudaMemsetAsync(d, 0, 64, 0));

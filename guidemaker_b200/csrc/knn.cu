@@ -26,33 +26,16 @@
 //   flood of insertions at the start of every split disappears.
 //
 // Merge kernel: k smallest keys over the splits of a query -> (int32 idx, uint8 dist) rows.
-#include "common.cuh"
-#include "distance.cuh"
+#include "knn_common.cuh"
 #include <new>
+#include <stdlib.h>
 
 namespace gm {
-
-int prof_begin(cudaStream_t s);
-void prof_end(int slot, cudaStream_t s, double pairs);
-
-static constexpr int CHUNK = 1024;      // targets per shared-memory stage (8 KB)
-static constexpr int NSTAGE = 3;
-static constexpr int THREADS = 128;
-static constexpr int MAX_SPLITS = 64;
-static constexpr uint32_t KEY_EMPTY = 0xFFFFFFFFu;
-static constexpr int IDX_BITS = 27;
-
-struct Index {
-    uint2 *planes = nullptr;
-    int64_t n_u = 0, n_pad = 0;
-    int L = 0, metric = 0;
-    void *ws = nullptr;
-    size_t ws_bytes = 0;
-};
 
 static int g_tune_r = 8;
 static int g_tune_splits = 0;
 static int g_tune_warm = -1;
+static int g_tune_engine = 1;          // 1 = K3b tcgen05 one-hot GEMM (tensor pipe, default), 0 = K3a XOR/POPC (INT pipes)
 
 // ---- small kernels -------------------------------------------------------------------------------
 
@@ -60,49 +43,6 @@ __global__ void to_planes_kernel(const uint64_t *__restrict__ g, int64_t n, int6
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
     out[i] = i < n ? to_planes(g[i]) : make_uint2(0u, 0u);
-}
-
-// ---- list maintenance ------------------------------------------------------------------------------
-
-// Insert key into the thread-private ascending list if it beats the current worst entry.
-// Returns the distance of the (new) worst entry, 31 while the list is not full.
-__device__ __noinline__ uint32_t list_insert(uint32_t *__restrict__ lst, int k, uint32_t key) {
-    uint32_t worst = lst[k - 1];
-    if (key < worst) {
-        int pos = k - 1;
-        while (pos > 0) {
-            uint32_t v = lst[pos - 1];
-            if (v <= key) break;
-            lst[pos] = v;
-            pos--;
-        }
-        lst[pos] = key;
-        worst = lst[k - 1];
-    }
-    return worst >> IDX_BITS;
-}
-
-// bias constant of the packed threshold test: byte = 128 + (tau - 1); after subtracting a distance
-// p <= 27 the byte keeps bit 7 iff p <= tau - 1, i.e. p < tau.  Bytes stay within [100, 158]: no
-// borrow ever crosses a byte boundary.
-__device__ __forceinline__ uint32_t bias_of(uint32_t tau) { return 0x7F7F7F7Fu + tau * 0x01010101u; }
-
-struct ScanArgs {
-    const uint2 *tplanes;
-    int n_chunks;             // chunks to cover (ceil(n_scan / CHUNK))
-    int chunks_per_split;
-    int64_t n_u;              // targets beyond this index are padding
-    const uint2 *qplanes;
-    int64_t q, q_pad;
-    int k;
-    uint32_t *lists;          // [gridDim.y][q_pad][k]
-    const uint32_t *warm;     // [q_pad][k] lists of the warm-up launch or nullptr
-    int L;
-};
-
-__device__ __forceinline__ void issue_chunk(uint2 *dst, const uint2 *src, uint64_t *bar) {
-    mbar_expect_tx(bar, CHUNK * (uint32_t)sizeof(uint2));
-    bulk_g2s(dst, src, CHUNK * (uint32_t)sizeof(uint2), bar);
 }
 
 // ---- K3a: Hamming pair scan --------------------------------------------------------------------------
@@ -337,6 +277,7 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
 
     // queries per thread: Levenshtein keeps 2 more state words per pair, so it uses R=4
     const int R = ix->metric == GM_METRIC_HAMMING ? (g_tune_r == 4 ? 4 : 8) : 4;
+    const bool use_tc = g_tune_engine == 1 && ix->metric == GM_METRIC_HAMMING;
     const int QT = THREADS * R;
     const int64_t tiles = (q + QT - 1) / QT;
     const int64_t q_pad = tiles * QT;
@@ -345,8 +286,10 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     // target splits: enough CTAs for >= ~16 per SM so the last wave is a small fraction
     int splits = g_tune_splits;
     if (splits <= 0) {
-        const int64_t want = (int64_t)device_sm_count() * 16;
-        splits = (int)((want + tiles - 1) / tiles);
+        // K3a: >= 16 CTAs per SM; K3b: one resident CTA per SM, >= 6 CTAs per SM over the launch
+        const int64_t grid_x = use_tc ? q_pad / tc_query_tile() : tiles;
+        const int64_t want = (int64_t)device_sm_count() * (use_tc ? 6 : 16);
+        splits = (int)((want + grid_x - 1) / grid_x);
     }
     if (splits > n_chunks) splits = n_chunks;
     if (splits > MAX_SPLITS) splits = MAX_SPLITS;
@@ -380,6 +323,14 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     a.q_pad = q_pad;
     a.k = k;
     a.L = ix->L;
+    a.dbg = nullptr;
+    static unsigned long long *d_dbg = nullptr;
+    const char *dbg_env = getenv("GM_TC_DEBUG");
+    const bool dbg_on = use_tc && dbg_env && dbg_env[0] == '1';
+    if (dbg_on) {
+        if (!d_dbg) GM_CUDA(cudaMalloc(&d_dbg, 64 * sizeof(unsigned long long)));
+        GM_CUDA(cudaMemsetAsync(d_dbg, 0, 64 * sizeof(unsigned long long), st));
+    }
 
     double pairs = 0.0;
     const int slot = prof_begin(st);
@@ -396,7 +347,20 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     a.chunks_per_split = cps;
     a.lists = lists;
     a.warm = wlists;
-    if (R == 8) launch_scan<8>(ix->metric, dim3((unsigned)tiles, (unsigned)splits), st, a);
+    if (use_tc) {
+        a.dbg = dbg_on ? d_dbg : nullptr;
+        rc = launch_hamming_tc(dim3((unsigned)(q_pad / tc_query_tile()), (unsigned)splits), st, a);
+        if (rc) return rc;
+        if (dbg_on) {
+            unsigned long long h[64];
+            GM_CUDA(cudaStreamSynchronize(st));
+            GM_CUDA(cudaMemcpy(h, d_dbg, sizeof h, cudaMemcpyDeviceToHost));
+            const double nt = h[5] ? (double)h[5] : 1.0;
+            fprintf(stderr, "[tc_dbg per tile] epi: total %.0f wait_full %.0f ld_wait %.0f cand %.0f arrive %.0f (cand_calls %llu) | prod: total %.0f wait_empty %.0f expand %.0f fence %.0f arrive %.0f | mma: total %.0f wait_bfull %.0f wait_accempty %.0f | tiles %llu\n",
+                    h[0] / nt, h[1] / nt, h[2] / nt, h[3] / nt, h[6] / nt, h[4], h[8] / nt, h[9] / nt, h[10] / nt, h[11] / nt, h[12] / nt,
+                    h[16] / nt, h[17] / nt, h[18] / nt, h[5]);
+        }
+    } else if (R == 8) launch_scan<8>(ix->metric, dim3((unsigned)tiles, (unsigned)splits), st, a);
     else launch_scan<4>(ix->metric, dim3((unsigned)tiles, (unsigned)splits), st, a);
     pairs += (double)q * (double)ix->n_u;
     prof_end(slot, st, pairs);
@@ -410,6 +374,12 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
 }  // namespace gm
 
 using namespace gm;
+
+extern "C" int gm_knn_engine(int engine) {
+    GM_ARG(engine == 0 || engine == 1, "gm_knn_engine: 0 = XOR/POPC (INT pipe), 1 = tcgen05 one-hot GEMM (tensor pipe)");
+    g_tune_engine = engine;
+    return GM_OK;
+}
 
 extern "C" int gm_knn_tune(int queries_per_thread, int splits, int warm_sample) {
     GM_ARG(queries_per_thread == 0 || queries_per_thread == 4 || queries_per_thread == 8, "gm_knn_tune: queries_per_thread must be 4 or 8");

@@ -1,0 +1,77 @@
+// knn_common.cuh -- declarations shared by the pair-scan kernels (knn.cu: K3a/K4, knn_tc.cu: K3b).
+#pragma once
+#include "common.cuh"
+#include "distance.cuh"
+
+namespace gm {
+
+int prof_begin(cudaStream_t s);
+void prof_end(int slot, cudaStream_t s, double pairs);
+
+static constexpr int CHUNK = 1024;      // targets per shared-memory stage (8 KB)
+static constexpr int NSTAGE = 3;
+static constexpr int THREADS = 128;
+static constexpr int MAX_SPLITS = 64;
+static constexpr uint32_t KEY_EMPTY = 0xFFFFFFFFu;
+static constexpr int IDX_BITS = 27;
+
+struct Index {
+    uint2 *planes = nullptr;
+    int64_t n_u = 0, n_pad = 0;
+    int L = 0, metric = 0;
+    void *ws = nullptr;
+    size_t ws_bytes = 0;
+};
+
+
+// ---- list maintenance ------------------------------------------------------------------------------
+
+// Insert key into the thread-private ascending list if it beats the current worst entry.
+// Returns the distance of the (new) worst entry, 31 while the list is not full.
+static __device__ __noinline__ uint32_t list_insert(uint32_t *__restrict__ lst, int k, uint32_t key) {
+    uint32_t worst = lst[k - 1];
+    if (key < worst) {
+        int pos = k - 1;
+        while (pos > 0) {
+            uint32_t v = lst[pos - 1];
+            if (v <= key) break;
+            lst[pos] = v;
+            pos--;
+        }
+        lst[pos] = key;
+        worst = lst[k - 1];
+    }
+    return worst >> IDX_BITS;
+}
+
+// bias constant of the packed threshold test: byte = 128 + (tau - 1); after subtracting a distance
+// p <= 27 the byte keeps bit 7 iff p <= tau - 1, i.e. p < tau.  Bytes stay within [100, 158]: no
+// borrow ever crosses a byte boundary.
+__device__ __forceinline__ uint32_t bias_of(uint32_t tau) { return 0x7F7F7F7Fu + tau * 0x01010101u; }
+
+struct ScanArgs {
+    const uint2 *tplanes;
+    int n_chunks;             // chunks to cover (ceil(n_scan / CHUNK))
+    int chunks_per_split;
+    int64_t n_u;              // targets beyond this index are padding
+    const uint2 *qplanes;
+    int64_t q, q_pad;
+    int k;
+    uint32_t *lists;          // [gridDim.y][q_pad][k]
+    const uint32_t *warm;     // [q_pad][k] lists of the warm-up launch or nullptr
+    int L;
+    unsigned long long *dbg;  // optional per-role cycle counters of block (0,0) (GM_TC_DEBUG=1), else nullptr
+};
+
+__device__ __forceinline__ void issue_chunk(uint2 *dst, const uint2 *src, uint64_t *bar) {
+    mbar_expect_tx(bar, CHUNK * (uint32_t)sizeof(uint2));
+    bulk_g2s(dst, src, CHUNK * (uint32_t)sizeof(uint2), bar);
+}
+
+
+// K3b launcher (knn_tc.cu): same contract as the K3a scan launch
+int launch_hamming_tc(dim3 grid, cudaStream_t st, const ScanArgs &a);
+int tc_query_tile();
+int microbench_mma_i8(double *ops_per_s);
+
+}  // namespace gm

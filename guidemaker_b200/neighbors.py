@@ -76,14 +76,18 @@ class NeighborMap(Mapping):
     def __init__(self, qcodes: np.ndarray, idx: np.ndarray, dist: np.ndarray, uniq: np.ndarray, L: int):
         # keep the first row of every distinct query guide, in order of first appearance (a dict
         # keyed by the guide string does exactly that; later rows carry identical values)
-        _, first = np.unique(qcodes, return_index=True)
-        first.sort()
-        self.codes = np.ascontiguousarray(qcodes[first])
-        self.idx = idx[first]
-        self.dist = dist[first]
+        order = np.argsort(qcodes, kind="stable")            # one sort serves dedupe and lookup
+        srt = qcodes[order]
+        head = np.ones(len(srt), dtype=bool)
+        head[1:] = srt[1:] != srt[:-1]
+        first_rows = order[head]                             # stable sort: smallest row of each group
+        self._sorted = srt[head]                             # distinct codes, ascending
+        kept = np.sort(first_rows)
+        self._pos = np.searchsorted(kept, first_rows)        # distinct code -> row of the kept arrays
+        self.codes = np.ascontiguousarray(qcodes[kept])
+        self.idx = idx[kept]
+        self.dist = dist[kept]
         self.uniq, self.L = uniq, int(L)
-        self._order = np.argsort(self.codes, kind="stable")
-        self._sorted = self.codes[self._order]
 
     def _row(self, seq) -> int:
         if not isinstance(seq, str) or len(seq) != self.L:
@@ -94,7 +98,7 @@ class NeighborMap(Mapping):
             return -1
         j = int(np.searchsorted(self._sorted, code))
         if j < len(self._sorted) and self._sorted[j] == code:
-            return int(self._order[j])
+            return int(self._pos[j])
         return -1
 
     def __getitem__(self, seq):

@@ -114,9 +114,14 @@ int gm_prof_read(double *scan_kernel_ms, int64_t *scan_kernel_launches, double *
 /* tuning knob for experiments and tests: queries per thread (4 or 8), target splits (0 = auto),
  * warm-start sample size (0 = off, -1 = default) */
 int gm_knn_tune(int queries_per_thread, int splits, int warm_sample);
+/* Hamming pair-scan engine: 1 = K3b tcgen05 kind::i8 one-hot GEMM with the threshold test on the TMEM read-out
+ * (default, ~3x faster), 0 = K3a XOR/POPC on the INT pipes.  Both are exact and return identical bits; the
+ * Levenshtein metric always uses its own INT-pipe kernel.  DESIGN.md section 3. */
+int gm_knn_engine(int engine);
 
-/* register-resident microbenchmarks used as roofline denominators:
- * what = 0: POPC, 1: LOP3, 2: IMAD.  Returns lane-operations per second over the whole GPU. */
+/* microbenchmarks used as roofline denominators, whole GPU:
+ * what = 0: POPC, 1: LOP3, 2: IMAD -> register-resident lane-operations per second;
+ * what = 3: back-to-back tcgen05.mma kind::i8 (128x256x32) -> int8 tensor operations per second (2 per MAC). */
 int gm_microbench(int what, double *ops_per_s);
 
 #ifdef __cplusplus

@@ -9,11 +9,21 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
-def capi():
+def capi_mod():
     from guidemaker_b200 import _capi
     _capi.init(0)
     yield _capi
     _capi.knn_tune(8, 0, -1)
+    _capi.knn_engine(1)
+
+
+@pytest.fixture
+def capi(capi_mod):
+    """the INT-pipe engine (K3a XOR/POPC) for the Hamming tests of this section; K3b has its own section below"""
+    capi_mod.knn_engine(0)
+    yield capi_mod
+    capi_mod.knn_engine(1)
+    capi_mod.knn_tune(8, 0, -1)
 
 
 def rand_guides(rng, n, L, n_base=None):
@@ -182,6 +192,71 @@ def test_knn_hamming_tuning_variants_agree(capi, tune):
         capi.knn_tune(8, 0, -1)
 
 
+# ---- K3b: tcgen05 one-hot GEMM engine --------------------------------------------------------------------------
+@pytest.fixture
+def tc_engine(capi_mod):
+    capi_mod.knn_engine(1)
+    yield capi_mod
+    capi_mod.knn_engine(1)
+    capi_mod.knn_tune(8, 0, -1)
+
+
+@pytest.mark.parametrize("L", [1, 4, 10, 16, 17, 20, 24, 27])
+def test_knn_tc_lengths_and_ragged_sizes(tc_engine, L):
+    rng = np.random.default_rng(700 + L)
+    for n_t, n_q in ((1, 1), (3, 7), (255, 257), (1023, 1025), (1024, 300), (5000, 3333)):
+        t, _ = O.unique_first_order(rand_guides(rng, n_t, L))
+        q = rand_guides(rng, n_q, L)
+        check_knn(tc_engine, t, q, L, 0, 5)
+
+
+@pytest.mark.parametrize("k", [1, 3, 20])
+def test_knn_tc_carsonella_all_vs_all(tc_engine, k, carsonella):
+    g, *_ = O.c_pam_scan(carsonella[1].encode(), "NGG", False, 20)
+    uniq, _ = O.unique_first_order(g)
+    check_knn(tc_engine, uniq, g, 20, 0, k)
+
+
+@pytest.mark.parametrize("tune", [(8, 1, 0), (8, 3, 0), (4, 7, 2048), (8, 64, 1024), (8, 0, 4096)])
+def test_knn_tc_splits_and_warm_start_agree(tc_engine, tune):
+    rng = np.random.default_rng(98)
+    t, _ = O.unique_first_order(rand_guides(rng, 70000, 20, n_base=60000))
+    q = rand_guides(rng, 3000, 20)
+    tc_engine.knn_tune(*tune)
+    check_knn(tc_engine, t, q, 20, 0, 6)
+
+
+def test_knn_tc_ties_and_duplicates(tc_engine):
+    L = 20
+    q = O.pack("A" * L)
+    t = []
+    for pos in range(L):
+        for b in "CGT":
+            s = ["A"] * L; s[pos] = b; t.append("".join(s))
+    t = O.pack_many(t)
+    check_knn(tc_engine, t, np.array([q] * 300, np.uint64), L, 0, 7)
+    check_knn(tc_engine, t[::-1].copy(), t, L, 0, 10)
+    same = np.full(3000, O.pack("ACGTACGTACGTACGTACGT"), np.uint64)        # all-equal queries against a tiny table
+    check_knn(tc_engine, t[:5], same, L, 0, 8)
+
+
+def test_knn_tc_equals_popc_engine_at_scale(capi_mod):
+    """both engines, 200k x 200k: byte-identical outputs"""
+    capi = capi_mod
+    rng = np.random.default_rng(11)
+    t, _ = O.unique_first_order(rand_guides(rng, 200000, 20, n_base=190000))
+    q = rand_guides(rng, 200000, 20)
+    ix = capi.Index(t, 20, 0)
+    capi.knn_engine(0)
+    a = ix.knn(q, 5)
+    capi.knn_engine(1)
+    b = ix.knn(q, 5)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    rows = rng.integers(0, len(q), size=200)
+    oi, od = O.c_knn(t, q[rows], 20, 0, 5)
+    assert np.array_equal(b[0][rows], oi) and np.array_equal(b[1][rows], od)
+
+
 # ---- K4 ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("L", [10, 20, 23, 27])
 def test_knn_leven_vs_oracle(capi, L):
@@ -230,9 +305,12 @@ def test_argument_errors(capi):
 
 
 # ---- BASELINE-size property checks ---------------------------------------------------------------------------
-def test_knn_hamming_config2_scale_properties(capi):
+@pytest.mark.parametrize("engine", [1, 0])
+def test_knn_hamming_config2_scale_properties(capi_mod, engine):
     """configs[1] scale (6.3 Mb, 66 % GC, NGG 3prime, L=20): sample-checked against the oracle plus
     size-independent properties over all rows."""
+    capi = capi_mod
+    capi.knn_engine(engine)
     rng = np.random.default_rng(2)
     seq = rand_genome(rng, 6_300_000, gc=0.66, n_frac=0.0005, lower_frac=0)
     g, s, p, nf, nr = capi.pam_scan(seq, "NGG", False, 20)

@@ -37,12 +37,13 @@ def main():
     ix = _capi.Index(uniq, 20, 0)
     _capi.prof_enable(True)
     rows = []
-    variants = [(8, 0, -1), (4, 0, -1), (8, 1, -1), (8, 2, -1), (8, 4, -1), (8, 8, -1), (8, 0, 0), (8, 0, 1024), (8, 0, 16384), (4, 4, -1)]
+    variants = [(8, 0, -1, 0), (8, 0, -1, 1), (8, 1, -1, 1), (8, 2, -1, 1), (8, 4, -1, 1), (8, 0, 0, 1), (8, 0, 16384, 1)]
     if len(sys.argv) > 1:
         variants = [tuple(int(x) for x in v.split(",")) for v in sys.argv[1:]]
     ref = None
-    for (r, sp, warm) in variants:
+    for (r, sp, warm, eng) in variants:
         _capi.knn_tune(r, sp, warm)
+        _capi.knn_engine(eng)
         for rep in range(2):
             _capi.prof_reset()
             t0 = time.time()
@@ -53,7 +54,7 @@ def main():
             ref = (idx, dist)
         same = bool(np.array_equal(ref[0], idx) and np.array_equal(ref[1], dist))
         rate = pr["pairs"] / (pr["scan_kernel_ms"] * 1e-3)
-        rows.append({"R": r, "splits": sp, "warm": warm, "scan_ms": pr["scan_kernel_ms"], "wall_s": wall, "pairs_per_s": rate, "same": same})
+        rows.append({"engine": eng, "R": r, "splits": sp, "warm": warm, "scan_ms": pr["scan_kernel_ms"], "wall_s": wall, "pairs_per_s": rate, "same": same})
         print(rows[-1], flush=True)
     out["variants"] = rows
     os.makedirs("gpurun_out", exist_ok=True)

@@ -13,6 +13,7 @@ _capi.init(0)
 name = sys.argv[1] if len(sys.argv) > 1 else "c2_bacterial_6.3Mb"
 metric = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 nq = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+engine = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 recs = config_genome(name)
 buf = b"N".join(r.seq.encode() for r in recs)
 g, s, p, nf, nr = _capi.pam_scan(buf, "NGG", False, 20)
@@ -21,6 +22,7 @@ uniq = np.ascontiguousarray(g[first == np.arange(len(g))])
 dup = _capi.seed_dedup(g, 20, 10, False)
 q = g if nq <= 0 else g[:nq]
 ix = _capi.Index(uniq, 20, metric)
+_capi.knn_engine(engine)
 for _ in range(2):
     idx, dist = ix.knn(q, 5)
 print("ok", len(g), len(uniq), int(dup.sum()), int(dist[:, 1].min()))

@@ -35,6 +35,50 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
                    "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                          \
                  : "r"(taddr))
 
+#define TMEM_LD_X32_PACK(r, taddr)                                                                                \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15," \
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                       \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), \
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),       \
+                   "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),     \
+                   "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),     \
+                   "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                          \
+                 : "r"(taddr))
+
+// packed 16-bit read: 32 registers per load cover 64 columns.  Also reports how the two columns land in a register.
+__global__ void __launch_bounds__(256) k_tmem_bw_pack(unsigned long long *cycles, uint32_t *sink, int iters, int nwarps) {
+    __shared__ uint32_t s_base;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) tmem_alloc(&s_base, 512);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t addr = s_base + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t acc = 0;
+    uint32_t a[32], b[32];
+    __syncthreads();
+    const long long t0 = clock64();
+    if (warp < nwarps) {
+        for (int it = 0; it < iters; it++) {
+            for (int col = 0; col < 512; col += 128) {
+                TMEM_LD_X32_PACK(a, addr + col);
+                TMEM_LD_X32_PACK(b, addr + col + 64);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) acc |= a[i] | a[i + 1];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) acc |= b[i] | b[i + 1];
+            }
+        }
+    }
+    const long long t1 = clock64();
+    if (acc == 0x12345678u) sink[0] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(s_base, 512);
+}
+
 // ---- probe 1: TMEM read bandwidth -------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_tmem_bw(unsigned long long *cycles, uint32_t *sink, int iters, int inflight) {
     __shared__ uint32_t s_base;
@@ -188,6 +232,21 @@ int main() {
             printf("tmem_read: grid %4d, %d x32 loads in flight: %.1f cycles per 256 KB sweep -> %.1f B/clk/SM\n", grid, inflight,
                    avg / iters, bytes / avg);
         }
+    }
+
+    for (int nwarps : {4, 8}) {
+        const int iters = 2000;
+        k_tmem_bw_pack<<<sms, 256>>>(d_cyc, d_sink, iters, nwarps);
+        CK(cudaDeviceSynchronize());
+        std::vector<unsigned long long> c(sms);
+        CK(cudaMemcpy(c.data(), d_cyc, sizeof(unsigned long long) * sms, cudaMemcpyDeviceToHost));
+        double avg = 0; for (auto v : c) avg += (double)v; avg /= sms;
+        const double cols = (double)nwarps * 32 * 512 * iters;             // lane-columns read
+        printf("tmem_read pack::16b: %d warps, 2 loads (64 cols each) in flight: %.1f cycles per sweep -> %.1f lane-columns/clk/SM (= %.1f B/clk/SM of 32-bit cells)\n",
+               nwarps, avg / iters, cols / avg, 4.0 * cols / avg);
+    }
+    for (int inflight : {4}) {
+        // 8 warps (two per lane quadrant) with unpacked loads, for comparison
     }
 
     // ---- probe 2
