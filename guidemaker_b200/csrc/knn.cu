@@ -328,8 +328,8 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     const char *dbg_env = getenv("GM_TC_DEBUG");
     const bool dbg_on = use_tc && dbg_env && dbg_env[0] == '1';
     if (dbg_on) {
-        if (!d_dbg) GM_CUDA(cudaMalloc(&d_dbg, 64 * sizeof(unsigned long long)));
-        GM_CUDA(cudaMemsetAsync(d_dbg, 0, 64 * sizeof(unsigned long long), st));
+        if (!d_dbg) GM_CUDA(cudaMalloc(&d_dbg, 256 * sizeof(unsigned long long)));
+        GM_CUDA(cudaMemsetAsync(d_dbg, 0, 256 * sizeof(unsigned long long), st));
     }
 
     double pairs = 0.0;
@@ -352,13 +352,23 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
         rc = launch_hamming_tc(dim3((unsigned)(q_pad / tc_query_tile()), (unsigned)splits), st, a);
         if (rc) return rc;
         if (dbg_on) {
-            unsigned long long h[64];
+            unsigned long long h[256];
             GM_CUDA(cudaStreamSynchronize(st));
             GM_CUDA(cudaMemcpy(h, d_dbg, sizeof h, cudaMemcpyDeviceToHost));
             const double nt = h[5] ? (double)h[5] : 1.0;
             fprintf(stderr, "[tc_dbg per tile] epi: total %.0f wait_full %.0f ld_wait %.0f cand %.0f arrive %.0f (cand_calls %llu) | prod: total %.0f wait_empty %.0f expand %.0f fence %.0f arrive %.0f | mma: total %.0f wait_bfull %.0f wait_accempty %.0f | tiles %llu\n",
                     h[0] / nt, h[1] / nt, h[2] / nt, h[3] / nt, h[6] / nt, h[4], h[8] / nt, h[9] / nt, h[10] / nt, h[11] / nt, h[12] / nt,
                     h[16] / nt, h[17] / nt, h[18] / nt, h[5]);
+            const char *names[5] = {"epi0", "epi1", "prod", "mma0", "mma1"};
+            unsigned long long base = h[64 + 2 * 32];          // producer tile 0 event 0
+            for (int r = 0; r < 5; r++) {
+                fprintf(stderr, "[tc_tl] %s:", names[r]);
+                for (int t = 0; t < 8; t++) {
+                    fprintf(stderr, " |");
+                    for (int e = 0; e < 4; e++) { unsigned long long v = h[64 + r * 32 + t * 4 + e]; fprintf(stderr, " %lld", v ? (long long)(v - base) : -1LL); }
+                }
+                fprintf(stderr, "\n");
+            }
         }
     } else if (R == 8) launch_scan<8>(ix->metric, dim3((unsigned)tiles, (unsigned)splits), st, a);
     else launch_scan<4>(ix->metric, dim3((unsigned)tiles, (unsigned)splits), st, a);

@@ -30,14 +30,35 @@
 
 namespace gm {
 
+// Shape of the pipeline.  Measured on B200 (tools/probes/tc_probe.cu, GM_TC_DEBUG=1): issuing a tcgen05.mma costs
+// ~65 cycles whatever its N and a tcgen05.commit ~95, and TMEM read-out scales with the number of reading warps.
+//   shape 2 (default): TWO query tiles per CTA, N = 128, 2 x 2 x 128 accumulator columns, 8 epilogue warps, 2 MMA
+//                      issuer warps                                   -> 140 ms on the 6.3 Mb config (1.33e13 cmp/s)
+//   shape 1          : ONE query tile, N = 256, 2 x 256 columns, 4 epilogue warps, 8 producer warps: half the MMA
+//                      instructions per comparison, but four warps cannot drain TMEM fast enough next to the running
+//                      MMA                                            -> 209 ms
+#ifndef GM_TC_SHAPE
+#define GM_TC_SHAPE 2
+#endif
 static constexpr int TC_M = 128;
-static constexpr int TC_SETS = 2;          // independent query tiles per CTA, one accumulator buffer + 4 epilogue warps each
-static constexpr int TC_QT = 256 * TC_SETS;   // queries per CTA (2 per row, 128 rows per set)
-static constexpr int TC_N = 128;           // targets per MMA tile: 2 query tiles x 2 accumulator buffers x 128 columns = 512 TMEM columns
+#if GM_TC_SHAPE == 1
+static constexpr int TC_SETS = 1;          // query tiles per CTA
+static constexpr int TC_N = 256;           // targets per MMA tile
+static constexpr int TC_PROD_WARPS = 8;    // one target per producer thread per tile
+static constexpr int TC_STAGES = 3;
+#else
+static constexpr int TC_SETS = 2;
+static constexpr int TC_N = 128;
+static constexpr int TC_PROD_WARPS = 4;
 static constexpr int TC_STAGES = 4;
+#endif
+static constexpr int TC_QT = 256 * TC_SETS;   // queries per CTA (2 per row, 128 rows per query tile)
 static constexpr int TC_RING = 8;          // raw-plane ring depth >= TC_STAGES + 2 (power of two), see the kernel header
-static constexpr int TC_MMA_WARP = 4 * TC_SETS + 4;        // first of TC_SETS MMA-issuer warps (one per query tile)
+static constexpr int TC_PROD_WARP0 = 4 * TC_SETS;                  // epilogue warps come first (TMEM lane quadrant = warp % 4)
+static constexpr int TC_MMA_WARP = TC_PROD_WARP0 + TC_PROD_WARPS;  // first of TC_SETS MMA-issuer warps (one per query tile)
 static constexpr int TC_THREADS = 32 * (TC_MMA_WARP + TC_SETS);
+static_assert(TC_SETS * 2 * TC_N == 512, "accumulator buffers must tile the 512 TMEM columns");
+static_assert(TC_N % 128 == 0, "the epilogue reads 128 columns per round");
 static constexpr uint32_t TC_FLAGS = 0x08200820u;   // bit 5 / bit 11 of both 16-bit halves of a packed register
 
 int tc_query_tile() { return TC_QT; }
@@ -105,8 +126,20 @@ __device__ __forceinline__ uint4 onehot_chunk(uint32_t eA, uint32_t eC, uint32_t
     return make_uint4(nibble_bytes(eA, j), nibble_bytes(eC, j), nibble_bytes(eG, j), nibble_bytes(eT, j));
 }
 
+// Per-role cycle counters and a short event timeline of block (0,0); compiled in only with -DGM_TC_INSTRUMENT
+// (then enabled at run time by GM_TC_DEBUG=1).  They are what the numbers in the header and DESIGN.md come from.
+#ifdef GM_TC_INSTRUMENT
+#define TC_TL_FIRST 2000
+#define TC_TL(role, i, ev) do { if (dbg && (i) >= TC_TL_FIRST && (i) < TC_TL_FIRST + 8) a.dbg[64 + (role) * 32 + ((i) - TC_TL_FIRST) * 4 + (ev)] = (unsigned long long)clock64(); } while (0)
 #define TC_T0(v) long long v = dbg ? clock64() : 0
 #define TC_ADD(acc, v) do { if (dbg) acc += (unsigned long long)(clock64() - v); } while (0)
+#define TC_DBG_ON (a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)
+#else
+#define TC_TL(role, i, ev) do { } while (0)
+#define TC_T0(v) do { } while (0)
+#define TC_ADD(acc, v) do { } while (0)
+#define TC_DBG_ON false
+#endif
 
 struct TcState {            // per epilogue thread: its two queries
     uint32_t qlo[2], qhi[2], tau[2];
@@ -185,7 +218,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool dbg = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+    const bool dbg = TC_DBG_ON;
     const long long t_start = dbg ? clock64() : 0;
     const int L = a.L;
     const int nd = (L + 3) >> 2;                      // data chunks; chunk nd carries the bias bytes
@@ -206,7 +239,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
     if (tid == 0) {
         // arrivals: one elected lane per warp (4 producer warps / 4 epilogue warps per set); b_empty gets one
         // tcgen05.commit from each MMA issuer
-        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&b_full[s], 4); mbar_init(&b_empty[s], TC_SETS); }
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&b_full[s], TC_PROD_WARPS); mbar_init(&b_empty[s], TC_SETS); }
         for (int q = 0; q < TC_SETS; q++)
             for (int b = 0; b < 2; b++) { mbar_init(&acc_full[q][b], 1); mbar_init(&acc_empty[q][b], 4); }
         mbar_fence_init();
@@ -215,7 +248,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
 
     // ---- A tiles: set s, row r = query (qbase + 256 s + r) * 1 + query (qbase + 256 s + 128 + r) * 64 ------------
     TcState st;
-    const int set = warp >> 2;                        // valid for the epilogue warps 0..7
+    const int set = warp >> 2;                        // valid for the epilogue warps
     const int row = tid & 127;
     if (warp < 4 * TC_SETS) {
         uint32_t e[2][4];
@@ -262,39 +295,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
         uint32_t ra[32], rb[32];
         for (int i = 0; i < n_tiles; i++) {
             const int buf = i & 1;
+            TC_TL(set, i, 3);
             { TC_T0(tw); mbar_wait(&acc_full[set][buf], (uint32_t)((i >> 1) & 1)); TC_ADD(c_wait, tw); }
+            TC_TL(set, i, 0);
             tc_fence_after();
             const uint32_t taddr = lane_addr + (uint32_t)buf * TC_N;
             const uint32_t t0 = (uint32_t)(tile0 + i) * TC_N;
             const uint2 *ring_tile = ring + (size_t)(i & (TC_RING - 1)) * TC_N;
-            TC_LD_X32_PACK(ra, taddr);                              // columns 0..63 of the tile
-            TC_LD_X32_PACK(rb, taddr + 64);                         // columns 64..127
-            { TC_T0(tw); tc_wait_ld(); TC_ADD(c_ld, tw); }
-            uint32_t f = 0;
+#pragma unroll 1
+            for (int h = 0; h < TC_N; h += 128) {                   // 128 columns per round: two packed loads in flight
+                TC_LD_X32_PACK(ra, taddr + h);                      // columns h .. h+63
+                TC_LD_X32_PACK(rb, taddr + h + 64);                 // columns h+64 .. h+127
+                { TC_T0(tw); tc_wait_ld(); TC_ADD(c_ld, tw); }
+                uint32_t f = 0;
 #pragma unroll
-            for (int x = 0; x < 32; x += 2) f |= ra[x] | ra[x + 1];
-            uint32_t fl = __ballot_sync(0xFFFFFFFFu, (f & TC_FLAGS) != 0);
-            if (fl) {
-                TC_T0(tw);
-                tc_candidates(fl, t0, ring_tile, st, a.k, (uint32_t)a.n_u, bias_bytes, L, lane);
-                tc_candidates(fl, t0 + 32, ring_tile + 32, st, a.k, (uint32_t)a.n_u, bias_bytes, L, lane);
-                TC_ADD(c_cand, tw); n_cand++;
-            }
-            f = 0;
+                for (int x = 0; x < 32; x += 2) f |= ra[x] | ra[x + 1];
+                uint32_t fl = __ballot_sync(0xFFFFFFFFu, (f & TC_FLAGS) != 0);
+                if (fl) {
+                    TC_T0(tw);
+                    tc_candidates(fl, t0 + h, ring_tile + h, st, a.k, (uint32_t)a.n_u, bias_bytes, L, lane);
+                    tc_candidates(fl, t0 + h + 32, ring_tile + h + 32, st, a.k, (uint32_t)a.n_u, bias_bytes, L, lane);
+                    TC_ADD(c_cand, tw); n_cand++;
+                }
+                f = 0;
 #pragma unroll
-            for (int x = 0; x < 32; x += 2) f |= rb[x] | rb[x + 1];
-            fl = __ballot_sync(0xFFFFFFFFu, (f & TC_FLAGS) != 0);
-            if (fl) {
-                TC_T0(tw);
-                tc_candidates(fl, t0 + 64, ring_tile + 64, st, a.k, (uint32_t)a.n_u, bias_bytes, L, lane);
-                tc_candidates(fl, t0 + 96, ring_tile + 96, st, a.k, (uint32_t)a.n_u, bias_bytes, L, lane);
-                TC_ADD(c_cand, tw); n_cand++;
+                for (int x = 0; x < 32; x += 2) f |= rb[x] | rb[x + 1];
+                fl = __ballot_sync(0xFFFFFFFFu, (f & TC_FLAGS) != 0);
+                if (fl) {
+                    TC_T0(tw);
+                    tc_candidates(fl, t0 + h + 64, ring_tile + h + 64, st, a.k, (uint32_t)a.n_u, bias_bytes, L, lane);
+                    tc_candidates(fl, t0 + h + 96, ring_tile + h + 96, st, a.k, (uint32_t)a.n_u, bias_bytes, L, lane);
+                    TC_ADD(c_cand, tw); n_cand++;
+                }
             }
+            TC_TL(set, i, 1);
             TC_T0(ta);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[set][buf]);
             TC_ADD(c_arr, ta);
+            TC_TL(set, i, 2);
         }
 #pragma unroll
         for (int s = 0; s < 2; s++) {                               // publish the finished lists
@@ -309,12 +349,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
     } else if (warp < TC_MMA_WARP) {
         unsigned long long c_wait = 0, c_exp = 0, c_fence = 0, c_arr = 0;
         // ================= producers: planes -> one-hot B tile (one target per thread) =========================
-        const int p = tid - 128 * TC_SETS;
+        static_assert(TC_N == 32 * TC_PROD_WARPS, "one target per producer thread per tile");
+        const int p = tid - 32 * TC_PROD_WARP0;
         uint2 tnext = a.tplanes[(size_t)tile0 * TC_N + p];
         for (int i = 0; i < n_tiles; i++) {
             const int s = i % TC_STAGES;
             const uint32_t round = (uint32_t)(i / TC_STAGES);
             if (round > 0) { TC_T0(tw); mbar_wait(&b_empty[s], (round - 1) & 1u); TC_ADD(c_wait, tw); }
+            TC_TL(2, i, 0);
             const uint2 tp = tnext;
             if (i + 1 < n_tiles) tnext = a.tplanes[(size_t)(tile0 + i + 1) * TC_N + p];   // prefetch the next tile's planes
             uint8_t *dst = sB + (size_t)s * b_bytes;
@@ -329,6 +371,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
                 *reinterpret_cast<uint4 *>(dstp + j * (TC_N * 16)) = w;
             }
             TC_ADD(c_exp, te);
+            TC_TL(2, i, 1);
             TC_T0(tf);
             fence_async_smem();                                     // generic-proxy writes -> visible to the tensor core
             TC_ADD(c_fence, tf);
@@ -336,8 +379,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
             __syncwarp();
             if (lane == 0) mbar_arrive(&b_full[s]);
             TC_ADD(c_arr, ta);
+            TC_TL(2, i, 2);
         }
-        if (dbg && tid == 128 * TC_SETS) { a.dbg[8] = (unsigned long long)(clock64() - t_role); a.dbg[9] = c_wait; a.dbg[10] = c_exp; a.dbg[11] = c_fence; a.dbg[12] = c_arr; }
+        if (dbg && tid == 32 * TC_PROD_WARP0) { a.dbg[8] = (unsigned long long)(clock64() - t_role); a.dbg[9] = c_wait; a.dbg[10] = c_exp; a.dbg[11] = c_fence; a.dbg[12] = c_arr; }
     } else {
         // ================= MMA issuers: warp TC_MMA_WARP + q feeds query tile q (one thread each) ====================
         const int q = warp - TC_MMA_WARP;
@@ -354,7 +398,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
             for (int i = 0; i < n_tiles; i++) {
                 const int buf = i & 1;
                 { TC_T0(tw); mbar_wait(&b_full[s], full_parity); TC_ADD(c_wb, tw); }
+                TC_TL(3 + q, i, 0);
                 if (i >= 2) { TC_T0(tw); mbar_wait(&acc_empty[q][buf], (uint32_t)(((i >> 1) - 1) & 1)); TC_ADD(c_wa, tw); }
+                TC_TL(3 + q, i, 1);
                 tc_fence_after();
                 const uint32_t d = tmem + (uint32_t)q * (2 * TC_N) + (uint32_t)buf * TC_N;
                 const uint64_t db = db0 + (uint64_t)((uint32_t)s * b_stage);
@@ -363,6 +409,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
                     tc_mma_i8(d, da + (uint64_t)((uint32_t)ks * a_ks), db + (uint64_t)((uint32_t)ks * b_ks), idesc, ks > 0 ? 1u : 0u);
                 tc_commit(&acc_full[q][buf]);                       // accumulator tile ready for this set's epilogue warps
                 tc_commit(&b_empty[s]);                             // this issuer is done with the smem stage
+                TC_TL(3 + q, i, 2);
                 if (++s == TC_STAGES) { s = 0; full_parity ^= 1u; }
             }
             if (dbg && q == 0) { a.dbg[16] = (unsigned long long)(clock64() - t_role); a.dbg[17] = c_wb; a.dbg[18] = c_wa; }

@@ -209,6 +209,56 @@ __global__ void __launch_bounds__(128) k_mma_i8(const int8_t *A, const int8_t *B
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// ---- probe 3: issue cost of the K3b pattern: per "tile" n_ks accumulating MMAs (M=128, N=ncols) + n_commit commits ----
+__global__ void __launch_bounds__(128) k_issue_pattern(int n_tiles, int ncols, int n_ks, int n_commit, int vary_desc, unsigned long long *out, int poll_mode = 0) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[8];
+    __shared__ uint32_t s_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 64 * 1024 / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x01010101u;
+    if (tid == 0) {
+        for (int b = 0; b < 8; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[b])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[6])) : "memory");   // bars[6]: phase 0 complete
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) tmem_alloc(&s_base, 512);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    if (tid == 0) {
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(PM >> 4) << 24);
+        const uint64_t da0 = make_desc(smem_u32(smem), PM * 16, 128);
+        const uint64_t db0 = make_desc(smem_u32(smem) + 16384, ncols * 16, 128);
+        long long t_issue = 0, t_poll = 0;
+        const long long t0 = clock64();
+        int stage = 0;
+        for (int i = 0; i < n_tiles; i++) {
+            const uint32_t d = s_base + (uint32_t)(i & 1) * 256;
+            const uint64_t db = vary_desc ? db0 + (uint64_t)(stage * 256) : db0;
+            const long long ti = clock64();
+            for (int ks = 0; ks < n_ks; ks++)
+                mma_i8(d, da0 + (uint64_t)(ks * 256), db + (uint64_t)(ks * 64), idesc, ks > 0 ? 1u : 0u);
+            for (int c = 0; c < n_commit; c++) mma_commit(&bars[(i * 2 + c) % 6]);
+            t_issue += clock64() - ti;
+            if (poll_mode == 1) { const long long tp = clock64(); (void)mbar_try(&bars[6], 0); t_poll += clock64() - tp; }
+            if (poll_mode == 2) { const long long tp = clock64(); volatile uint32_t *f = (volatile uint32_t *)&s_base; (void)*f; t_poll += clock64() - tp; }
+            if (++stage == 4) stage = 0;
+        }
+        const long long t1 = clock64();
+        mma_commit(&bars[7]);
+        out[0] = (unsigned long long)(t1 - t0);
+        out[1] = (unsigned long long)t_issue;
+        out[2] = (unsigned long long)t_poll;
+    }
+    __syncthreads();
+    // drain: wait generously for the tensor pipe before freeing TMEM
+    if (tid == 0) { long long t = clock64(); while (clock64() - t < 4000000) { } }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(s_base, 512);
+}
+
 int main() {
     int dev = 0, sms = 0, khz = 0;
     CK(cudaSetDevice(dev));
@@ -247,6 +297,26 @@ int main() {
     }
     for (int inflight : {4}) {
         // 8 warps (two per lane quadrant) with unpacked loads, for comparison
+    }
+
+    // ---- probe 3
+    CK(cudaFuncSetAttribute(k_issue_pattern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    struct { int ncols, n_ks, n_commit, vary; } pats[] = {{128, 3, 2, 1}, {128, 3, 2, 0}, {128, 3, 1, 1}, {128, 3, 0, 1}, {256, 3, 2, 1}, {128, 1, 2, 1}, {128, 6, 2, 1}, {64, 3, 2, 1}};
+    for (auto &pt : pats) {
+        const int n_tiles = 2000;
+        k_issue_pattern<<<1, 128, 80 * 1024>>>(n_tiles, pt.ncols, pt.n_ks, pt.n_commit, pt.vary, d_cyc);
+        CK(cudaDeviceSynchronize());
+        unsigned long long c[2]; CK(cudaMemcpy(c, d_cyc, 16, cudaMemcpyDeviceToHost));
+        printf("issue pattern N=%3d, %d MMAs + %d commits per tile, %s descriptors: %.1f clk per tile (issue section %.1f)\n", pt.ncols, pt.n_ks,
+               pt.n_commit, pt.vary ? "varying" : "constant", (double)c[0] / n_tiles, (double)c[1] / n_tiles);
+    }
+    for (int poll = 1; poll <= 2; poll++) for (int ncm = 0; ncm <= 1; ncm++) {
+        const int n_tiles = 2000;
+        k_issue_pattern<<<1, 128, 80 * 1024>>>(n_tiles, 128, 3, ncm, 1, d_cyc, poll);
+        CK(cudaDeviceSynchronize());
+        unsigned long long c[3]; CK(cudaMemcpy(c, d_cyc, 24, cudaMemcpyDeviceToHost));
+        printf("after 3 MMAs + %d commit: %s on an already-complete barrier/flag costs %.1f clk (tile %.1f, issue %.1f)\n", ncm,
+               poll == 1 ? "mbarrier.try_wait" : "ld.volatile.shared", (double)c[2] / n_tiles, (double)c[0] / n_tiles, (double)c[1] / n_tiles);
     }
 
     // ---- probe 2
