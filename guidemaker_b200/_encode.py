@@ -49,11 +49,13 @@ def encode_matrix(mat: np.ndarray) -> np.ndarray:
     n, L = mat.shape
     if L > 27:
         raise ValueError("guides longer than 27 nt are not supported (got %d)" % L)
-    codes = _LUT[mat]
-    if n and codes.max(initial=0) > 3:
-        raise ValueError("guide sequences may contain only A, C, G, T")
     if n == 0 or L == 0:
         return np.zeros(n, dtype=np.uint64)
+    seen = np.flatnonzero(np.bincount(mat.reshape(-1), minlength=256))
+    if (_LUT[seen] > 3).any():
+        raise ValueError("guide sequences may contain only A, C, G, T")
+    x = (mat >> 1) & 3                                    # A:0 C:1 G:3 T:2
+    codes = x ^ (x >> 1)                                  # A:0 C:1 G:2 T:3
     planes = []
     for bit in (0, 1):                                   # bit planes via packbits, then interleave
         b = np.packbits((codes >> bit) & 1, axis=1, bitorder="little")

@@ -82,8 +82,11 @@ class NeighborMap(Mapping):
         head[1:] = srt[1:] != srt[:-1]
         first_rows = order[head]                             # stable sort: smallest row of each group
         self._sorted = srt[head]                             # distinct codes, ascending
-        kept = np.sort(first_rows)
-        self._pos = np.searchsorted(kept, first_rows)        # distinct code -> row of the kept arrays
+        keep_mask = np.zeros(len(qcodes), dtype=bool)
+        keep_mask[first_rows] = True
+        kept = np.flatnonzero(keep_mask)                     # first rows in ascending (= first-appearance) order
+        rank = np.cumsum(keep_mask, dtype=np.int64) - 1
+        self._pos = rank[first_rows]                         # distinct code -> row of the kept arrays
         self.codes = np.ascontiguousarray(qcodes[kept])
         self.idx = idx[kept]
         self.dist = dist[kept]
