@@ -195,7 +195,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     _capi.init(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=__import__("datetime").timedelta(seconds=120))
     dev = torch.device("cuda", local_rank)
 
     def barrier():
@@ -396,6 +396,8 @@ def run_ours(args):
 
 
 def main():
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

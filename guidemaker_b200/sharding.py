@@ -11,7 +11,13 @@ import numpy as np
 
 
 def world():
-    """(rank, world_size) of the initialised torch.distributed group, else (0, 1)."""
+    """(rank, world_size) of the initialised torch.distributed group, else (0, 1).
+
+    torch is consulted only if the caller has already imported it: without that there cannot be an initialised
+    process group, and importing torch here would add seconds to a single-GPU run."""
+    import sys
+    if "torch" not in sys.modules:
+        return 0, 1
     try:
         import torch.distributed as dist
     except ImportError:  # pragma: no cover

@@ -40,7 +40,7 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=__import__("datetime").timedelta(seconds=120))
     _capi.init(local_rank)
 
     cfg = tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False)
