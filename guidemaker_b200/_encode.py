@@ -69,13 +69,18 @@ def encode_guides(seqs, L: int | None = None) -> np.ndarray:
     return encode_matrix(as_byte_matrix(seqs, L))
 
 
+# byte of a guide2bit word (4 bases) -> the 4 ASCII letters, little endian (base order = byte order)
+_LUT4 = np.zeros(256, dtype="<u4")
+for _b in range(256):
+    _LUT4[_b] = sum(int(_ASCII[(_b >> (2 * _j)) & 3]) << (8 * _j) for _j in range(4))
+
+
 def decode_matrix(g: np.ndarray, L: int) -> np.ndarray:
-    """uint64 guide2bit -> (N, L) uint8 ASCII matrix."""
-    g = np.asarray(g, dtype=np.uint64)
-    out = np.empty((len(g), L), dtype=np.uint8)
-    for i in range(L):
-        out[:, i] = _ASCII[((g >> np.uint64(2 * i)) & np.uint64(3)).astype(np.intp)]
-    return out
+    """uint64 guide2bit -> (N, L) uint8 ASCII matrix (one table look-up per 4 bases)."""
+    g = np.ascontiguousarray(g, dtype="<u8")
+    nb = (L + 3) // 4
+    quads = _LUT4[g.view(np.uint8).reshape(len(g), 8)[:, :nb]]          # (N, nb) uint32 = 4 letters each
+    return np.ascontiguousarray(quads.view(np.uint8).reshape(len(g), 4 * nb)[:, :L])
 
 
 def decode_guides(g: np.ndarray, L: int) -> np.ndarray:

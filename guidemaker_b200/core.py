@@ -27,6 +27,7 @@ from __future__ import annotations
 import hashlib
 import logging
 import statistics
+import zlib
 from copy import deepcopy
 from itertools import product
 from typing import List
@@ -134,8 +135,9 @@ class PamTarget:
         start = (gstart.astype(np.int64) - rec_start[rec])
 
         seq30 = self._target_seq30(np.frombuffer(buf, np.uint8), seqs, rec, rec_start, lens, start, strand, five, P, L)
+        target_mat = decode_matrix(guides, L)
         df = pd.DataFrame({
-            "target": _str_series(decode_matrix(guides, L)),
+            "target": _str_series(target_mat),
             "exact_pam": pd.Categorical(_str_series(decode_matrix(pamcode.astype(np.uint64), P))),
             "start": start.astype(np.uint32),
             "stop": (start + L).astype(np.uint32),
@@ -152,6 +154,9 @@ class PamTarget:
         df["hasrestrictionsite"] = np.nan
         df["isseedduplicated"] = True
         df["dtype"] = pd.Categorical.from_codes(np.zeros(n, dtype=np.int8), categories=[self.dtype])
+        # The packed guides ride along so that TargetProcessor need not re-encode n strings; they are used only if
+        # the CRC of the `target` column's bytes still matches (any edit, filter or reorder of the frame voids them).
+        df.attrs["_gm_packed"] = {"crc": zlib.crc32(target_mat), "shape": target_mat.shape, "guides": guides}
         return df
 
     @staticmethod
@@ -226,7 +231,13 @@ class TargetProcessor:
         cache = getattr(self, "_packed_cache", None)
         if cache is None or cache[0] != key:
             mat = self._guide_matrix()
-            cache = (key, encode_matrix(mat), mat.shape[1], col.array)   # keep the array alive: ids stay unique
+            stash = self.targets.attrs.get("_gm_packed") if isinstance(self.targets.attrs, dict) else None
+            if (stash is not None and tuple(stash.get("shape", ())) == mat.shape and len(stash["guides"]) == len(mat)
+                    and stash.get("crc") == zlib.crc32(np.ascontiguousarray(mat))):
+                guides = stash["guides"]                       # produced by find_targets for exactly these strings
+            else:
+                guides = encode_matrix(mat)
+            cache = (key, guides, mat.shape[1], col.array)      # keep the array alive: ids stay unique
             self._packed_cache = cache
         return cache[1], cache[2]
 
@@ -253,6 +264,7 @@ class TargetProcessor:
     def find_unique_near_pam(self) -> None:
         """seedseq = PAM-proximal ``lsr`` nt; isseedduplicated = keep-first duplicate flag (core.py:388-416)."""
         self.targets = deepcopy(self.targets)
+        guides, _ = self._packed()
         mat = self._guide_matrix()
         L = mat.shape[1]
         five = bool(self.pam_orientation)
@@ -266,7 +278,6 @@ class TargetProcessor:
             if cut < 0:
                 cut = max(L + cut, 0)
             seed, lsr_eff = mat[:, cut:], L - cut
-        guides = encode_matrix(mat)
         self.targets['seedseq'] = _str_series(np.ascontiguousarray(seed), index=self.targets.index)
         self.targets['isseedduplicated'] = _capi.seed_dedup(guides, L, lsr_eff if lsr_eff < L else 0, five)
         col = self.targets['target']
@@ -286,6 +297,8 @@ class TargetProcessor:
         uniq = np.ascontiguousarray(guides[is_first])
         metric = _capi.METRIC_HAMMING if self._is_hamming() else _capi.METRIC_LEVEN
         self.nmslib_index = ExactIndex(uniq, L, metric)
+        # row -> index of its guide in the distinct-guide table (valid while the packed cache is)
+        self._row2uniq = (self._packed_cache[0], (np.cumsum(is_first, dtype=np.int64) - 1)[first_row])
 
     def get_neighbors(self, configpath, num_threads=2) -> None:
         """k nearest guides of every query row; keep a query iff its nearest OTHER guide is at least
@@ -306,7 +319,11 @@ class TargetProcessor:
         if dist.shape[1] < 2 or (idx[:, 1] < 0).any():
             raise IndexError("list index out of range")    # editdist[1] with fewer than 2 hits (core.py:512,518)
         keep = dist[:, 1] >= int(self.editdist)
-        self.neighbors = NeighborMap(q[keep], idx[keep], dist[keep], index.uniq, L)
+        group = None
+        r2u = getattr(self, "_row2uniq", None)
+        if r2u is not None and r2u[0] == self._packed_cache[0] and len(r2u[1]) == len(guides) and index.uniq is self.nmslib_index.uniq:
+            group = r2u[1][qmask][keep]
+        self.neighbors = NeighborMap(q[keep], idx[keep], dist[keep], index.uniq, L, group=group)
 
     def export_bed(self) -> object:
         """Rows with a first-seen seed as a BED-like frame sorted by (chrom, start) (core.py:525-543)."""

@@ -73,24 +73,36 @@ class ExactIndex:
 class NeighborMap(Mapping):
     """``neighbors[seq] -> {"target": seq, "neighbors": {"seqs": [...], "dist": [...]}}``."""
 
-    def __init__(self, qcodes: np.ndarray, idx: np.ndarray, dist: np.ndarray, uniq: np.ndarray, L: int):
-        # keep the first row of every distinct query guide, in order of first appearance (a dict
-        # keyed by the guide string does exactly that; later rows carry identical values)
-        order = np.argsort(qcodes, kind="stable")            # one sort serves dedupe and lookup
-        srt = qcodes[order]
-        head = np.ones(len(srt), dtype=bool)
-        head[1:] = srt[1:] != srt[:-1]
-        first_rows = order[head]                             # stable sort: smallest row of each group
-        self._sorted = srt[head]                             # distinct codes, ascending
-        keep_mask = np.zeros(len(qcodes), dtype=bool)
-        keep_mask[first_rows] = True
-        kept = np.flatnonzero(keep_mask)                     # first rows in ascending (= first-appearance) order
-        rank = np.cumsum(keep_mask, dtype=np.int64) - 1
-        self._pos = rank[first_rows]                         # distinct code -> row of the kept arrays
+    def __init__(self, qcodes: np.ndarray, idx: np.ndarray, dist: np.ndarray, uniq: np.ndarray, L: int, group=None):
+        """qcodes/idx/dist: the kept query rows in row order.  A dict keyed by the guide string keeps the first row of
+        every distinct guide, in order of first appearance (later rows carry identical values).  `group[i]` = any
+        integer id < len(uniq) that is equal for equal guides (e.g. the row's index in the distinct-guide table): with
+        it the dedupe is a linear scatter; without it, one stable sort."""
+        n = len(qcodes)
+        if group is not None and n:
+            slot = np.full(len(uniq) if len(uniq) else 1, -1, dtype=np.int64)
+            rev = np.arange(n - 1, -1, -1, dtype=np.int64)
+            slot[np.asarray(group)[rev]] = rev               # repeated index: the last assignment wins = smallest row
+            kept = np.flatnonzero(slot[group] == np.arange(n))
+        else:
+            order = np.argsort(qcodes, kind="stable")
+            srt = qcodes[order]
+            head = np.ones(n, dtype=bool)
+            head[1:] = srt[1:] != srt[:-1]
+            keep_mask = np.zeros(n, dtype=bool)
+            keep_mask[order[head]] = True                    # stable sort: smallest row of each group
+            kept = np.flatnonzero(keep_mask)
         self.codes = np.ascontiguousarray(qcodes[kept])
         self.idx = idx[kept]
         self.dist = dist[kept]
         self.uniq, self.L = uniq, int(L)
+        self._sorted = self._pos = None                      # lookup index, built on first use
+
+    def _lookup_index(self):
+        if self._sorted is None:
+            self._pos = np.argsort(self.codes, kind="stable")
+            self._sorted = self.codes[self._pos]
+        return self._sorted, self._pos
 
     def _row(self, seq) -> int:
         if not isinstance(seq, str) or len(seq) != self.L:
@@ -99,9 +111,10 @@ class NeighborMap(Mapping):
             code = encode_guides([seq], self.L)[0]
         except ValueError:
             return -1
-        j = int(np.searchsorted(self._sorted, code))
-        if j < len(self._sorted) and self._sorted[j] == code:
-            return int(self._pos[j])
+        srt, pos = self._lookup_index()
+        j = int(np.searchsorted(srt, code))
+        if j < len(srt) and srt[j] == code:
+            return int(pos[j])
         return -1
 
     def __getitem__(self, seq):
