@@ -286,9 +286,10 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     // target splits: enough CTAs for >= ~16 per SM so the last wave is a small fraction
     int splits = g_tune_splits;
     if (splits <= 0) {
-        // K3a: >= 16 CTAs per SM; K3b: one resident CTA per SM, >= 6 CTAs per SM over the launch
+        // K3a: >= 16 CTAs per SM.  K3b: one resident CTA per SM and every split restarts with the loose warm-start
+        // thresholds (measured ~0.6 ms of SM time per extra CTA), so it only splits to reach ~2 CTAs per SM
         const int64_t grid_x = use_tc ? q_pad / tc_query_tile() : tiles;
-        const int64_t want = (int64_t)device_sm_count() * (use_tc ? 6 : 16);
+        const int64_t want = (int64_t)device_sm_count() * (use_tc ? 2 : 16);
         splits = (int)((want + grid_x - 1) / grid_x);
     }
     if (splits > n_chunks) splits = n_chunks;

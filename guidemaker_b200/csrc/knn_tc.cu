@@ -171,13 +171,13 @@ __device__ __noinline__ uint32_t list_insert_smem(uint32_t *lst, int k, uint32_t
 // which targets beat its thresholds; the owner inserts them in ascending index into its shared-memory lists.
 // No loop over registers, no divergence, a few dozen instructions per event.
 __device__ __noinline__ void tc_candidates(uint32_t flagged, uint32_t t0, const uint2 *ring_chunk, TcState &s, int k, uint32_t n_u,
-                                              uint8_t *bias_bytes, int L, int lane) {
+                                           uint8_t *bias_bytes, int L, int lane) {
     const uint2 tp = ring_chunk[lane];
     const bool valid = t0 + (uint32_t)lane < n_u;
     while (flagged) {
         const int src = __ffs(flagged) - 1;
         flagged &= flagged - 1;
-        uint32_t hits[2];
+        uint32_t hits[2];       // (evaluating only the query whose flag bit fired was measured: the extra shuffle costs more)
 #pragma unroll
         for (int e = 0; e < 2; e++) {
             const uint32_t ql = __shfl_sync(0xFFFFFFFFu, s.qlo[e], src), qh = __shfl_sync(0xFFFFFFFFu, s.qhi[e], src);
@@ -307,25 +307,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
                 TC_LD_X32_PACK(ra, taddr + h);                      // columns h .. h+63
                 TC_LD_X32_PACK(rb, taddr + h + 64);                 // columns h+64 .. h+127
                 { TC_T0(tw); tc_wait_ld(); TC_ADD(c_ld, tw); }
-                uint32_t f = 0;
+                // pack::16b puts adjacent columns in one register: registers 0..15 = columns 0..31, 16..31 = columns 32..63
 #pragma unroll
-                for (int x = 0; x < 32; x += 2) f |= ra[x] | ra[x + 1];
-                uint32_t fl = __ballot_sync(0xFFFFFFFFu, (f & TC_FLAGS) != 0);
-                if (fl) {
-                    TC_T0(tw);
-                    tc_candidates(fl, t0 + h, ring_tile + h, st, a.k, (uint32_t)a.n_u, bias_bytes, L, lane);
-                    tc_candidates(fl, t0 + h + 32, ring_tile + h + 32, st, a.k, (uint32_t)a.n_u, bias_bytes, L, lane);
-                    TC_ADD(c_cand, tw); n_cand++;
-                }
-                f = 0;
+                for (int half = 0; half < 4; half++) {
+                    const uint32_t *r = half < 2 ? ra : rb;
+                    const int o = (half & 1) * 16;
+                    uint32_t f = 0;
 #pragma unroll
-                for (int x = 0; x < 32; x += 2) f |= rb[x] | rb[x + 1];
-                fl = __ballot_sync(0xFFFFFFFFu, (f & TC_FLAGS) != 0);
-                if (fl) {
-                    TC_T0(tw);
-                    tc_candidates(fl, t0 + h + 64, ring_tile + h + 64, st, a.k, (uint32_t)a.n_u, bias_bytes, L, lane);
-                    tc_candidates(fl, t0 + h + 96, ring_tile + h + 96, st, a.k, (uint32_t)a.n_u, bias_bytes, L, lane);
-                    TC_ADD(c_cand, tw); n_cand++;
+                    for (int x = 0; x < 16; x += 2) f |= r[o + x] | r[o + x + 1];
+                    const uint32_t fl = __ballot_sync(0xFFFFFFFFu, (f & TC_FLAGS) != 0);
+                    if (fl) {
+                        TC_T0(tw);
+                        tc_candidates(fl, t0 + h + half * 32, ring_tile + h + half * 32, st, a.k, (uint32_t)a.n_u, bias_bytes, L, lane);
+                        TC_ADD(c_cand, tw);
+                    }
                 }
             }
             TC_TL(set, i, 1);
