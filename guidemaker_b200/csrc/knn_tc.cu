@@ -78,6 +78,15 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// one lane of a fully active warp (elect.sync): the issuing lane of the MMA warps
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_commit_addr(uint32_t bar_smem_addr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_smem_addr) : "memory");
+}
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -378,38 +387,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
         }
         if (dbg && tid == 32 * TC_PROD_WARP0) { a.dbg[8] = (unsigned long long)(clock64() - t_role); a.dbg[9] = c_wait; a.dbg[10] = c_exp; a.dbg[11] = c_fence; a.dbg[12] = c_arr; }
     } else {
-        // ================= MMA issuers: warp TC_MMA_WARP + q feeds query tile q (one thread each) ====================
-        const int q = warp - TC_MMA_WARP;
-        if (lane == 0) {
-            unsigned long long c_wb = 0, c_wa = 0;
-            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-            // descriptors differ only in the start-address field (low 14 bits, units of 16 bytes): build once, add offsets
-            const uint64_t da = tc_desc(smem_u32(sA) + (uint32_t)q * a_bytes, TC_M * 16, 128);
-            const uint64_t db0 = tc_desc(smem_u32(sB), TC_N * 16, 128);
-            const uint32_t a_ks = (2u * TC_M * 16u) >> 4, b_stage = b_bytes >> 4, b_ks = (2u * TC_N * 16u) >> 4;
-            constexpr int n_ks = kc / 2;
-            int s = 0;
-            uint32_t full_parity = 0;
-            for (int i = 0; i < n_tiles; i++) {
-                const int buf = i & 1;
-                { TC_T0(tw); mbar_wait(&b_full[s], full_parity); TC_ADD(c_wb, tw); }
-                TC_TL(3 + q, i, 0);
-                if (i >= 2) { TC_T0(tw); mbar_wait(&acc_empty[q][buf], (uint32_t)(((i >> 1) - 1) & 1)); TC_ADD(c_wa, tw); }
-                TC_TL(3 + q, i, 1);
-                tc_fence_after();
-                const uint32_t d = tmem + (uint32_t)q * (2 * TC_N) + (uint32_t)buf * TC_N;
-                const uint64_t db = db0 + (uint64_t)((uint32_t)s * b_stage);
+        // ================= MMA issuers: warp TC_MMA_WARP + q feeds query tile q ============================================
+        // The WHOLE warp runs this loop and every operand is made provably warp-uniform (__shfl_sync from lane 0), so the
+        // descriptors live in uniform registers and one elect.sync lane issues.  Issuing from `if (lane == 0)` made the
+        // compiler wrap every tcgen05.mma in an ELECT + 5 x R2UR.BROADCAST waterfall loop (~65 cycles per instruction).
+        const int q = __shfl_sync(0xFFFFFFFFu, warp, 0) - TC_MMA_WARP;
+        const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem, 0);
+        const uint32_t sA_u = __shfl_sync(0xFFFFFFFFu, smem_u32(sA), 0), sB_u = __shfl_sync(0xFFFFFFFFu, smem_u32(sB), 0);
+        const uint32_t bar_full_u = __shfl_sync(0xFFFFFFFFu, smem_u32(&acc_full[0][0]), 0);
+        const uint32_t bar_bempty_u = __shfl_sync(0xFFFFFFFFu, smem_u32(&b_empty[0]), 0);
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+        // descriptors differ only in the start-address field (low 14 bits, units of 16 bytes): build once, add offsets
+        const uint64_t da = tc_desc(sA_u + (uint32_t)q * a_bytes, TC_M * 16, 128);
+        const uint64_t db0 = tc_desc(sB_u, TC_N * 16, 128);
+        const uint32_t a_ks = (2u * TC_M * 16u) >> 4, b_stage = b_bytes >> 4, b_ks = (2u * TC_N * 16u) >> 4;
+        constexpr int n_ks = kc / 2;
+        const bool leader = elect_one();
+        unsigned long long c_wb = 0, c_wa = 0;
+        int s = 0;
+        uint32_t full_parity = 0;
+        for (int i = 0; i < n_tiles; i++) {
+            const int buf = i & 1;
+            { TC_T0(tw); mbar_wait(&b_full[s], full_parity); TC_ADD(c_wb, tw); }
+            TC_TL(3 + q, i, 0);
+            if (i >= 2) { TC_T0(tw); mbar_wait(&acc_empty[q][buf], (uint32_t)(((i >> 1) - 1) & 1)); TC_ADD(c_wa, tw); }
+            TC_TL(3 + q, i, 1);
+            tc_fence_after();
+            const uint32_t d = tmem_u + (uint32_t)q * (2 * TC_N) + (uint32_t)buf * TC_N;
+            const uint64_t db = db0 + (uint64_t)((uint32_t)s * b_stage);
+            const uint32_t bar_f = bar_full_u + (uint32_t)((q * 2 + buf) * 8), bar_e = bar_bempty_u + (uint32_t)(s * 8);
+            if (leader) {
 #pragma unroll
                 for (int ks = 0; ks < n_ks; ks++)
                     tc_mma_i8(d, da + (uint64_t)((uint32_t)ks * a_ks), db + (uint64_t)((uint32_t)ks * b_ks), idesc, ks > 0 ? 1u : 0u);
-                tc_commit(&acc_full[q][buf]);                       // accumulator tile ready for this set's epilogue warps
-                tc_commit(&b_empty[s]);                             // this issuer is done with the smem stage
-                TC_TL(3 + q, i, 2);
-                if (++s == TC_STAGES) { s = 0; full_parity ^= 1u; }
+                tc_commit_addr(bar_f);                              // accumulator tile ready for this set's epilogue warps
+                tc_commit_addr(bar_e);                              // this issuer is done with the smem stage
             }
-            if (dbg && q == 0) { a.dbg[16] = (unsigned long long)(clock64() - t_role); a.dbg[17] = c_wb; a.dbg[18] = c_wa; }
+            __syncwarp();
+            TC_TL(3 + q, i, 2);
+            if (++s == TC_STAGES) { s = 0; full_parity ^= 1u; }
         }
-        __syncwarp();
+        if (dbg && q == 0) { a.dbg[16] = (unsigned long long)(clock64() - t_role); a.dbg[17] = c_wb; a.dbg[18] = c_wa; }
     }
 
     const long long t_td = dbg ? clock64() : 0;
