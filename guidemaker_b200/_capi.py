@@ -57,6 +57,7 @@ def load_library(path: str = LIBPATH) -> ctypes.CDLL:
     """dlopen the engine and declare every prototype of include/gm_b200.h (no CUDA call is made)."""
     global _LIB
     if _LIB is None:
+        path = os.environ.get("GM_B200_LIB", path)        # kernel experiments: an alternative build of the same library
         if not os.path.exists(path):
             raise EngineUnavailable(
                 f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

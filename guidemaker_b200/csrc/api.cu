@@ -6,7 +6,7 @@
 
 #include "common.cuh"
 
-namespace gm { int microbench_mma_i8(double *ops_per_s); }
+namespace gm { int microbench_mma_i8(int variant, double *ops_per_s); }
 
 namespace gm {
 
@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(256) mb_kernel(uint32_t *out, int iters) {
 extern "C" int gm_microbench(int what, double *ops_per_s) {
     int rc = ensure_init();
     if (rc) return rc;
-    GM_ARG(what >= 0 && what <= 3 && ops_per_s, "gm_microbench: what must be 0..3");
-    if (what == 3) return microbench_mma_i8(ops_per_s);
+    GM_ARG(what >= 0 && what <= 6 && ops_per_s, "gm_microbench: what must be 0..6");
+    if (what >= 3) return microbench_mma_i8(what - 3, ops_per_s);
     uint32_t *d = nullptr;
     GM_CUDA(dev_alloc((void **)&d, 64, 0));
     GM_CUDA(cudaMemsetAsync(d, 0, 64, 0));

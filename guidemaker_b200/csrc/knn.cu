@@ -292,16 +292,19 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
         const int64_t want = (int64_t)device_sm_count() * (use_tc ? 2 : 16);
         splits = (int)((want + grid_x - 1) / grid_x);
     }
-    if (splits > n_chunks) splits = n_chunks;
-    if (splits > MAX_SPLITS) splits = MAX_SPLITS;
-    if (splits < 1) splits = 1;
-    int cps = (n_chunks + splits - 1) / splits;
-    splits = (n_chunks + cps - 1) / cps;
-
     // warm start: worthwhile only when the table is much larger than the sample
     int warm = g_tune_warm < 0 ? 4 * CHUNK : g_tune_warm;
     warm = (warm + CHUNK - 1) / CHUNK;                       // in chunks
     if (n_chunks < 16 * warm || ix->n_u < (int64_t)warm * CHUNK) warm = 0;
+    // K3b inherits the warm lists and scans only the chunks behind the sample; K3a rescans from chunk 0
+    const int first_chunk = use_tc ? warm : 0;
+    const int scan_chunks = n_chunks - first_chunk;
+
+    if (splits > scan_chunks) splits = scan_chunks;
+    if (splits > MAX_SPLITS) splits = MAX_SPLITS;
+    if (splits < 1) splits = 1;
+    int cps = (scan_chunks + splits - 1) / splits;
+    splits = (scan_chunks + cps - 1) / cps;
 
     const size_t qp_bytes = (size_t)q_pad * sizeof(uint2);
     const size_t list_bytes = (size_t)splits * q_pad * k * sizeof(uint32_t);
@@ -318,6 +321,8 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
 
     ScanArgs a;
     a.tplanes = ix->planes;
+    a.tperm = ix->planes_perm;
+    a.first_chunk = 0;
     a.n_u = ix->n_u;
     a.qplanes = qplanes;
     a.q = q;
@@ -346,6 +351,7 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     }
     a.n_chunks = n_chunks;
     a.chunks_per_split = cps;
+    a.first_chunk = first_chunk;
     a.lists = lists;
     a.warm = wlists;
     if (use_tc) {
@@ -353,27 +359,15 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
         rc = launch_hamming_tc(dim3((unsigned)(q_pad / tc_query_tile()), (unsigned)splits), st, a);
         if (rc) return rc;
         if (dbg_on) {
-            unsigned long long h[256];
+            unsigned long long h[2];
             GM_CUDA(cudaStreamSynchronize(st));
             GM_CUDA(cudaMemcpy(h, d_dbg, sizeof h, cudaMemcpyDeviceToHost));
-            const double nt = h[5] ? (double)h[5] : 1.0;
-            fprintf(stderr, "[tc_dbg per tile] epi: total %.0f wait_full %.0f ld_wait %.0f cand %.0f arrive %.0f (cand_calls %llu) | prod: total %.0f wait_empty %.0f expand %.0f fence %.0f arrive %.0f | mma: total %.0f wait_bfull %.0f wait_accempty %.0f | tiles %llu\n",
-                    h[0] / nt, h[1] / nt, h[2] / nt, h[3] / nt, h[6] / nt, h[4], h[8] / nt, h[9] / nt, h[10] / nt, h[11] / nt, h[12] / nt,
-                    h[16] / nt, h[17] / nt, h[18] / nt, h[5]);
-            const char *names[5] = {"epi0", "epi1", "prod", "mma0", "mma1"};
-            unsigned long long base = h[64 + 2 * 32];          // producer tile 0 event 0
-            for (int r = 0; r < 5; r++) {
-                fprintf(stderr, "[tc_tl] %s:", names[r]);
-                for (int t = 0; t < 8; t++) {
-                    fprintf(stderr, " |");
-                    for (int e = 0; e < 4; e++) { unsigned long long v = h[64 + r * 32 + t * 4 + e]; fprintf(stderr, " %lld", v ? (long long)(v - base) : -1LL); }
-                }
-                fprintf(stderr, "\n");
-            }
+            fprintf(stderr, "[tc_dbg] candidate events %llu (%.2f per query), list inserts %llu (%.2f per query), grid %u x %d\n", h[0],
+                    (double)h[0] / (double)q, h[1], (double)h[1] / (double)q, (unsigned)(q_pad / tc_query_tile()), splits);
         }
     } else if (R == 8) launch_scan<8>(ix->metric, dim3((unsigned)tiles, (unsigned)splits), st, a);
     else launch_scan<4>(ix->metric, dim3((unsigned)tiles, (unsigned)splits), st, a);
-    pairs += (double)q * (double)ix->n_u;
+    pairs += (double)q * ((double)ix->n_u - (double)first_chunk * CHUNK);
     prof_end(slot, st, pairs);
 
     knn_merge_kernel<<<(unsigned)((q + 127) / 128), 128, 0, st>>>(lists, splits, q, q_pad, k, d_idx, d_dist, dist_only);
@@ -426,6 +420,11 @@ extern "C" int gm_index_create_dev(const uint64_t *d_uniq2bit, int64_t n_u, int 
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) { dev_free(ix->planes, st); delete ix; return cuda_fail(e, "to_planes_kernel", __FILE__, __LINE__); }
+    if (metric == GM_METRIC_HAMMING) {               // K3b's bit order (knn_tc.cu)
+        e = dev_alloc((void **)&ix->planes_perm, (size_t)ix->n_pad * sizeof(uint2), st);
+        if (e == cudaSuccess) { tc_permute_planes(ix->planes, ix->n_pad, ix->planes_perm, st); e = cudaGetLastError(); }
+        if (e != cudaSuccess) { dev_free(ix->planes_perm, st); dev_free(ix->planes, st); delete ix; return cuda_fail(e, "tc_permute_planes", __FILE__, __LINE__); }
+    }
     *index = ix;
     return GM_OK;
 }
@@ -464,6 +463,7 @@ extern "C" int gm_index_free(void *index) {
     if (!ix) return GM_OK;
     cudaDeviceSynchronize();
     dev_free(ix->planes, 0);
+    dev_free(ix->planes_perm, 0);
     dev_free(ix->ws, 0);
     delete ix;
     return GM_OK;

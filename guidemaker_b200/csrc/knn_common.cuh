@@ -17,6 +17,7 @@ static constexpr int IDX_BITS = 27;
 
 struct Index {
     uint2 *planes = nullptr;
+    uint2 *planes_perm = nullptr;   // Hamming only: bit-permuted copy for K3b (knn_tc.cu, "Bit order")
     int64_t n_u = 0, n_pad = 0;
     int L = 0, metric = 0;
     void *ws = nullptr;
@@ -51,6 +52,8 @@ __device__ __forceinline__ uint32_t bias_of(uint32_t tau) { return 0x7F7F7F7Fu +
 
 struct ScanArgs {
     const uint2 *tplanes;
+    const uint2 *tperm;       // K3b: bit-permuted planes of the same table
+    int first_chunk;          // K3b: the scan starts here (behind the warm sample, whose lists split 0 inherits)
     int n_chunks;             // chunks to cover (ceil(n_scan / CHUNK))
     int chunks_per_split;
     int64_t n_u;              // targets beyond this index are padding
@@ -71,7 +74,8 @@ __device__ __forceinline__ void issue_chunk(uint2 *dst, const uint2 *src, uint64
 
 // K3b launcher (knn_tc.cu): same contract as the K3a scan launch
 int launch_hamming_tc(dim3 grid, cudaStream_t st, const ScanArgs &a);
+int tc_permute_planes(const uint2 *planes, int64_t n, uint2 *out, cudaStream_t st);
 int tc_query_tile();
-int microbench_mma_i8(double *ops_per_s);
+int microbench_mma_i8(int variant, double *ops_per_s);
 
 }  // namespace gm
