@@ -24,9 +24,11 @@
 //                then ORs/ballots; flagged chunks go into a small shared-memory queue as (first target, row mask).
 //   warps 16-23  producers, two groups of four taking alternate tiles: planes -> one-hot B tile (one target per
 //                thread), canonical no-swizzle K-major layout, then proxy fence + arrive.
-//   warps 24-25  one MMA issuer per set (elect.sync lane, operands in uniform registers); warp 24 owns the TMEM
-//                allocation; tcgen05.commit publishes accumulator buffers and releases shared-memory stages.
-//   warps 26-29  candidate warps: warp c serves the queues of TMEM quadrant c (both sets, both buffers) and is the
+//   warps 24-27  MMA issuers, one per (set, accumulator buffer) (elect.sync lane, operands in uniform registers): two
+//                try_waits, three MMAs and two tcgen05.commit (~95 cycles each) per tile are ~400 cycles of chain, more
+//                than the 384 cycles the tensor pipe needs for a tile, so an issuer only takes every other tile.  Warp 24
+//                owns the TMEM allocation; the commits publish accumulator buffers and release shared-memory stages.
+//   warps 28-31  candidate warps: warp c serves the queues of TMEM quadrant c (both sets, both buffers) and is the
 //                exclusive owner of the lists and bounds of those 128 queries.  Per event lane j loads target j of the
 //                chunk (L2), all 32 exact distances of a flagged row's two queries are evaluated at once (2 LOP3 + POPC),
 //                hits are inserted by full (distance, index) key into lists kept in shared memory (so the order in
@@ -42,7 +44,8 @@
 namespace gm {
 
 // Timing-only ablations (tools/tc_ablate.py; results are wrong by construction): 1 = epilogue skips the TMEM loads,
-// 2 = producers skip the one-hot expansion, 4 = issuers skip the MMAs (commits only), 8 = candidate path disabled.
+// 2 = producers skip the one-hot expansion, 4 = issuers skip the MMAs (commits only), 8 = candidate path disabled,
+// 16 = producers skip the proxy fence, 32 = producers do not wait for the stage to be released.
 #ifndef GM_TC_ABL
 #define GM_TC_ABL 0
 #endif
@@ -55,7 +58,8 @@ static constexpr int TC_EPI_WARPS = 8 * TC_SETS;                   // (set, buff
 static constexpr int TC_PROD_WARP0 = TC_EPI_WARPS;
 static constexpr int TC_PROD_WARPS = 8;                            // two groups of four, alternate tiles
 static constexpr int TC_MMA_WARP = TC_PROD_WARP0 + TC_PROD_WARPS;  // first of TC_SETS issuer warps
-static constexpr int TC_CAND_WARP0 = TC_MMA_WARP + TC_SETS;
+static constexpr int TC_MMA_WARPS = 2 * TC_SETS;                   // (set, buffer): each issues every other tile of its set
+static constexpr int TC_CAND_WARP0 = TC_MMA_WARP + TC_MMA_WARPS;
 static constexpr int TC_CAND_WARPS = 4;                            // one per TMEM lane quadrant
 static constexpr int TC_THREADS = 32 * (TC_CAND_WARP0 + TC_CAND_WARPS);
 static constexpr int TC_QN = 32;           // entries per candidate queue (power of two)
@@ -174,7 +178,7 @@ template <int kc /* 16-byte K chunks, even */>
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const ScanArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t b_full[TC_STAGES], b_empty[TC_STAGES], acc_full[TC_SETS][2], acc_empty[TC_SETS][2];
-    __shared__ uint32_t s_tmem, s_done;
+    __shared__ uint32_t s_tmem, s_done, s_issued[TC_SETS];
     __shared__ uint32_t q_head[TC_EPI_WARPS], q_tail[TC_EPI_WARPS];       // candidate queues: consumer / producer cursor
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -202,6 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
             for (int b = 0; b < 2; b++) { mbar_init(&acc_full[q][b], 1); mbar_init(&acc_empty[q][b], 4); }
         mbar_fence_init();
         s_done = 0;
+        for (int q = 0; q < TC_SETS; q++) s_issued[q] = 0;
     }
     if (tid < TC_EPI_WARPS) { q_head[tid] = 0; q_tail[tid] = 0; }
     if (warp == TC_MMA_WARP) tc_alloc(&s_tmem, 512);
@@ -324,7 +329,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
             const uint2 tp = tnext;
             if (i + 2 < n_tiles) tnext = tsrc[(size_t)(i + 2) * TC_N];       // prefetch this thread's next target
             const uint32_t eA = ~(tp.x | tp.y) & lmask, eC = tp.x & ~tp.y, eG = tp.y & ~tp.x, eT = tp.x & tp.y;
-            if (round > 0) mbar_wait(&b_empty[s], (round - 1) & 1u);
+            if (round > 0 && !(GM_TC_ABL & 32)) mbar_wait(&b_empty[s], (round - 1) & 1u);
             uint8_t *dstp = sB + (size_t)s * b_bytes + (size_t)p * 16;
 #pragma unroll
             for (int j = 0; j < ((GM_TC_ABL & 2) ? 0 : kc); j++) {  // positions beyond L have all-zero masks
@@ -332,19 +337,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
                 if (j == nd) w.x = 1u | (64u << 8);                 // multiplies the bias bytes of A: 1 * b1 + 64 * b2
                 *reinterpret_cast<uint4 *>(dstp + j * (TC_N * 16)) = w;
             }
-            fence_async_smem();                                     // generic-proxy writes -> visible to the tensor core
+            if (!(GM_TC_ABL & 16)) fence_async_smem();              // generic-proxy writes -> visible to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(&b_full[s]);
         }
     } else if (warp < TC_CAND_WARP0) {
-        // ================= MMA issuers: warp TC_MMA_WARP + q feeds set q ===================================================
+        // ================= MMA issuers: warp TC_MMA_WARP + 2 par + q issues tiles par, par + 2, .. of set q =============
         // The WHOLE warp runs this loop and every operand is made provably warp-uniform (__shfl_sync from lane 0), so the
         // descriptors live in uniform registers and one elect.sync lane issues.  Issuing from `if (lane == 0)` made the
         // compiler wrap every tcgen05.mma in an ELECT + 5 x R2UR.BROADCAST waterfall loop (~65 cycles per instruction).
-        const int q = __shfl_sync(0xFFFFFFFFu, warp, 0) - TC_MMA_WARP;
+        const int mw = __shfl_sync(0xFFFFFFFFu, warp, 0) - TC_MMA_WARP;
+        const int q = mw & 1, par = mw >> 1;
         const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem, 0);
         const uint32_t sA_u = __shfl_sync(0xFFFFFFFFu, smem_u32(sA), 0), sB_u = __shfl_sync(0xFFFFFFFFu, smem_u32(sB), 0);
-        const uint32_t bar_full_u = __shfl_sync(0xFFFFFFFFu, smem_u32(&acc_full[0][0]), 0);
+        const uint32_t bar_f = __shfl_sync(0xFFFFFFFFu, smem_u32(&acc_full[q][par]), 0);
         const uint32_t bar_bempty_u = __shfl_sync(0xFFFFFFFFu, smem_u32(&b_empty[0]), 0);
         const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
         // descriptors differ only in the start-address field (low 14 bits, units of 16 bytes): build once, add offsets
@@ -353,90 +359,112 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
         const uint32_t a_ks = (2u * TC_M * 16u) >> 4, b_stage = b_bytes >> 4, b_ks = (2u * TC_N * 16u) >> 4;
         constexpr int n_ks = kc / 2;
         const bool leader = elect_one();
-        int s = 0;
-        uint32_t full_parity = 0;
-        for (int i = 0; i < n_tiles; i++) {
-            const int buf = i & 1;
-            mbar_wait(&b_full[s], full_parity);
-            if (i >= 2) mbar_wait(&acc_empty[q][buf], (uint32_t)(((i >> 1) - 1) & 1));
+        const uint32_t d = tmem_u + (uint32_t)q * (2 * TC_N) + (uint32_t)par * TC_N;
+        for (int i = par; i < n_tiles; i += 2) {
+            const int s = i % TC_STAGES;
+            mbar_wait(&b_full[s], (uint32_t)((i / TC_STAGES) & 1));
+            if (i >= 2) mbar_wait(&acc_empty[q][par], (uint32_t)(((i >> 1) - 1) & 1));
+            // The two issuers of a set take turns: tiles enter the tensor pipe in ascending order, so the bias bytes an
+            // MMA reads can only reflect list entries from EARLIER tiles (lower target indices) -- what makes "flag iff
+            // strictly closer than the k-th best" exact under the (distance, index) order.
+            if (ld_vol(&s_issued[q]) != (uint32_t)i) {
+                const long long w0 = clock64();
+                while (ld_vol(&s_issued[q]) != (uint32_t)i)
+                    if (clock64() - w0 > 20000000000LL) { printf("libgm_b200: issue-order watchdog fired\n"); __trap(); }
+            }
             tc_fence_after();
-            const uint32_t d = tmem_u + (uint32_t)q * (2 * TC_N) + (uint32_t)buf * TC_N;
             const uint64_t db = db0 + (uint64_t)((uint32_t)s * b_stage);
-            const uint32_t bar_f = bar_full_u + (uint32_t)((q * 2 + buf) * 8), bar_e = bar_bempty_u + (uint32_t)(s * 8);
+            const uint32_t bar_e = bar_bempty_u + (uint32_t)(s * 8);
             if (leader) {
 #pragma unroll
                 for (int ks = 0; ks < ((GM_TC_ABL & 4) ? 0 : n_ks); ks++)
                     tc_mma_i8(d, da + (uint64_t)((uint32_t)ks * a_ks), db + (uint64_t)((uint32_t)ks * b_ks), idesc, ks > 0 ? 1u : 0u);
+                __threadfence_block();
+                st_vol(&s_issued[q], (uint32_t)i + 1u);             // the set's other issuer may go ahead
                 tc_commit_addr(bar_f);                              // accumulator buffer ready for its epilogue warps
                 tc_commit_addr(bar_e);                              // this issuer is done with the smem stage
             }
             __syncwarp();
-            if (++s == TC_STAGES) { s = 0; full_parity ^= 1u; }
         }
     } else {
         // ================= candidate warps: warp c owns the queries of TMEM quadrant c of both sets ====================
         const int c = warp - TC_CAND_WARP0;
         uint32_t head[4] = {0u, 0u, 0u, 0u};
         unsigned long long n_events = 0, n_inserts = 0;
-        for (;;) {
-            const uint32_t done = ld_vol(&s_done);                  // read BEFORE the scan: done + empty queues = finished
-            bool progressed = false;
+        // one event = (first target of a 32-target chunk, mask of flagged rows); `set` selects the A operand
+        auto serve = [&](const uint2 ev, const uint2 tp, const int set) {
+            uint32_t fl = ev.y;
+            const uint32_t kpart = ev.x + (uint32_t)lane;
+            const bool valid = (int64_t)kpart < a.n_u;
+            while (fl) {
+                const int row = c * 32 + (__ffs(fl) - 1);
+                fl &= fl - 1;
 #pragma unroll
-            for (int x = 0; x < 4; x++) {                           // x = (set, buffer)
-                const int qid = (x >> 1) * 8 + (x & 1) * 4 + c, set = x >> 1;
-                if (head[x] == ld_vol(&q_tail[qid])) continue;
-                __threadfence_block();
-                const uint2 ev = sQueue[qid * TC_QN + (head[x] & (TC_QN - 1))];
-                head[x]++;
-                __syncwarp();
-                if (lane == 0) st_vol(&q_head[qid], head[x]);       // entry copied: the slot may be reused
-                progressed = true;
-                n_events++;
-                const uint32_t t0 = ev.x;
-                uint32_t fl = ev.y;
-                const uint2 tp = a.tperm[(size_t)t0 + lane];
-                const uint32_t kpart = t0 + (uint32_t)lane;
-                const bool valid = (int64_t)kpart < a.n_u;
-                while (fl) {
-                    const int row = c * 32 + (__ffs(fl) - 1);
-                    fl &= fl - 1;
-#pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        const int qx = set * 256 + e * 128 + row;
-                        const uint2 qp = sQ[qx];
-                        uint32_t bound = sBound[qx];
-                        const uint32_t key = ((uint32_t)hamming_planes(qp.x, qp.y, tp.x, tp.y) << IDX_BITS) | kpart;
-                        uint32_t hits = __ballot_sync(0xFFFFFFFFu, valid && key < bound);
-                        if (hits == 0) continue;
-                        const uint32_t bound0 = bound;
-                        while (hits) {                              // ascending target index
-                            const int i = __ffs(hits) - 1;
-                            hits &= hits - 1;
-                            const uint32_t ki = __shfl_sync(0xFFFFFFFFu, key, i);
-                            if (ki < bound) {
-                                uint32_t w = 0;
-                                if (lane == 0) w = list_insert_smem(s_lists + qx, a.k, ki);
-                                w = __shfl_sync(0xFFFFFFFFu, w, 0);
-                                bound = min(bound, w);
-                                n_inserts++;
-                            }
+                for (int e = 0; e < 2; e++) {
+                    const int qx = set * 256 + e * 128 + row;
+                    const uint2 qp = sQ[qx];
+                    uint32_t bound = sBound[qx];
+                    const uint32_t key = ((uint32_t)hamming_planes(qp.x, qp.y, tp.x, tp.y) << IDX_BITS) | kpart;
+                    uint32_t hits = __ballot_sync(0xFFFFFFFFu, valid && key < bound);
+                    if (hits == 0) continue;
+                    const uint32_t bound0 = bound;
+                    while (hits) {                                  // ascending target index
+                        const int i = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        const uint32_t ki = __shfl_sync(0xFFFFFFFFu, key, i);
+                        if (ki < bound) {
+                            uint32_t w = 0;
+                            if (lane == 0) w = list_insert_smem(s_lists + qx, a.k, ki);
+                            w = __shfl_sync(0xFFFFFFFFu, w, 0);
+                            bound = min(bound, w);
+                            n_inserts++;
                         }
-                        if (bound != bound0 && lane == 0) {
-                            sBound[qx] = bound;
-                            if ((bound >> IDX_BITS) != (bound0 >> IDX_BITS)) {   // tighten the bias byte; later MMAs pick it up
-                                sA[(size_t)set * a_bytes + (size_t)nd * (TC_M * 16) + (size_t)row * 16 + e] =
-                                    (uint8_t)(31 - L + (int)(bound >> IDX_BITS));
-                                fence_async_smem();
-                            }
-                        }
-                        __syncwarp();
                     }
+                    if (bound != bound0 && lane == 0) {
+                        sBound[qx] = bound;
+                        if ((bound >> IDX_BITS) != (bound0 >> IDX_BITS)) {       // tighten the bias byte; later MMAs pick it up
+                            sA[(size_t)set * a_bytes + (size_t)nd * (TC_M * 16) + (size_t)row * 16 + e] =
+                                (uint8_t)(31 - L + (int)(bound >> IDX_BITS));
+                            fence_async_smem();
+                        }
+                    }
+                    __syncwarp();
                 }
             }
-            if (!progressed) {
+        };
+        for (;;) {
+            const uint32_t done = ld_vol(&s_done);                  // read BEFORE the scan: done + empty queues = finished
+            // take at most one event from each of the four queues (x = (set, buffer)) and issue their loads together
+            bool have[4];
+            bool any = false;
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                have[x] = head[x] != ld_vol(&q_tail[(x >> 1) * 8 + (x & 1) * 4 + c]);
+                any |= have[x];
+            }
+            if (!any) {
                 if (done == (uint32_t)TC_EPI_WARPS) break;
                 __nanosleep(32);
+                continue;
             }
+            __threadfence_block();
+            uint2 ev[4], tp[4];
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+                if (have[x]) {
+                    ev[x] = sQueue[((x >> 1) * 8 + (x & 1) * 4 + c) * TC_QN + (head[x] & (TC_QN - 1))];
+                    tp[x] = a.tperm[(size_t)ev[x].x + lane];
+                    head[x]++;
+                }
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+                    if (have[x]) st_vol(&q_head[(x >> 1) * 8 + (x & 1) * 4 + c], head[x]);   // entries copied: slots may be reused
+            }
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+                if (have[x]) { serve(ev[x], tp[x], x >> 1); n_events++; }
         }
         if (a.dbg && lane == 0) { atomicAdd(&a.dbg[0], n_events); atomicAdd(&a.dbg[1], n_inserts); }
     }
@@ -465,13 +493,13 @@ __device__ __forceinline__ void tc_mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-template <int N, bool A_TMEM>
+template <int N, bool A_TMEM, bool CYCLE = false>
 __global__ void __launch_bounds__(128, 1) mb_mma_i8_kernel(int n_mma, unsigned long long *cycles) {
     extern __shared__ __align__(1024) uint8_t smem[];          // operands: contents irrelevant for throughput
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t s_base;
     const int tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < (128 + 256) * 32 / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x01010101u;
+    for (int i = tid; i < (CYCLE ? 64 * 1024 : (128 + 256) * 32) / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x01010101u;
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     fence_async_smem();
     if (warp == 0) tc_alloc(&s_base, 512);
@@ -484,10 +512,16 @@ __global__ void __launch_bounds__(128, 1) mb_mma_i8_kernel(int n_mma, unsigned l
         const uint64_t da = tc_desc(smem_u32(smem), 128 * 16, 128), db = tc_desc(smem_u32(smem) + 128 * 32, N * 16, 128);
         t0 = clock64();
         // two accumulator tiles alternate so consecutive MMAs do not depend on each other
+        // CYCLE: like the kNN kernel, consecutive MMAs read different operand tiles (3 A tiles in the first 12 KB,
+        // 12 B tiles behind them), so no operand can be reused from one MMA to the next
+        int ia = 0, ib = 0;
         for (int i = 0; i < n_mma; i++) {
             const uint32_t d = s_base + (N == 128 ? (uint32_t)(i & 1) * 128u : 0u);
-            if (A_TMEM) tc_mma_i8_ts(d, s_base + 256, db, idesc, i > 1 ? 1u : 0u);
-            else tc_mma_i8(d, da, db, idesc, i > 1 ? 1u : 0u);
+            const uint64_t oa = CYCLE ? (uint64_t)(ia * (4096 >> 4)) : 0, ob = CYCLE ? (uint64_t)((3 + ib) * (4096 >> 4)) : 0;
+            if (A_TMEM) tc_mma_i8_ts(d, s_base + 256 + (CYCLE ? (uint32_t)ia * 8u : 0u), db + ob - (CYCLE ? 128 * 32 / 16 : 0), idesc, i > 1 ? 1u : 0u);
+            else tc_mma_i8(d, da + oa, db + ob - (CYCLE ? 128 * 32 / 16 : 0), idesc, i > 1 ? 1u : 0u);
+            if (++ia == 3) ia = 0;
+            if (++ib == 12) ib = 0;
         }
         tc_commit(&bar);
     }
@@ -500,11 +534,11 @@ __global__ void __launch_bounds__(128, 1) mb_mma_i8_kernel(int n_mma, unsigned l
 
 // int8 tensor ops/s (2 per MAC) of the whole GPU, timed with CUDA events.  variant 0: N = 256 SS (the roofline
 // denominator), 1: N = 128 SS, 2: N = 128 TS, 3: N = 256 TS (A operand in tensor memory).
-template <int N, bool A_TMEM>
+template <int N, bool A_TMEM, bool CYCLE = false>
 static int microbench_mma_i8_t(double *ops_per_s) {
     static bool attr_set = false;
     if (!attr_set) {
-        GM_CUDA(cudaFuncSetAttribute(mb_mma_i8_kernel<N, A_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+        GM_CUDA(cudaFuncSetAttribute(mb_mma_i8_kernel<N, A_TMEM, CYCLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
         attr_set = true;
     }
     unsigned long long *d = nullptr;
@@ -516,7 +550,7 @@ static int microbench_mma_i8_t(double *ops_per_s) {
     float best = 1e30f;
     for (int rep = 0; rep < 3; rep++) {
         GM_CUDA(cudaEventRecord(e0));
-        mb_mma_i8_kernel<N, A_TMEM><<<grid, 128, 116 * 1024>>>(n_mma, d);      // > half the SM's shared memory: one CTA per SM
+        mb_mma_i8_kernel<N, A_TMEM, CYCLE><<<grid, 128, 116 * 1024>>>(n_mma, d);      // > half the SM's shared memory: one CTA per SM
         count_launch();
         GM_CUDA(cudaEventRecord(e1));
         GM_CUDA(cudaEventSynchronize(e1));
@@ -536,6 +570,8 @@ int microbench_mma_i8(int variant, double *ops_per_s) {
     case 1: return microbench_mma_i8_t<128, false>(ops_per_s);
     case 2: return microbench_mma_i8_t<128, true>(ops_per_s);
     case 3: return microbench_mma_i8_t<256, true>(ops_per_s);
+    case 4: return microbench_mma_i8_t<128, false, true>(ops_per_s);
+    case 5: return microbench_mma_i8_t<128, true, true>(ops_per_s);
     default: return microbench_mma_i8_t<256, false>(ops_per_s);
     }
 }

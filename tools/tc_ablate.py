@@ -44,6 +44,8 @@ def child():
     uniq = np.ascontiguousarray(g[first == np.arange(len(g))])
     ix = _capi.Index(uniq, 20, 0)
     _capi.prof_enable(True)
+    if os.environ.get("ABL_WARM"):
+        _capi.knn_tune(8, 0, int(os.environ["ABL_WARM"]))
     res = {}
     ref = None
     for eng in ((0, 1) if os.environ.get("ABL_CHECK", "1") == "1" else (1,)):
@@ -70,6 +72,8 @@ def run(names):
         env = dict(os.environ, GM_B200_LIB=os.path.join(VAR, f"libgm_{lib}.so"))
         if opt == "dbg":
             env["GM_TC_DEBUG"] = "1"
+        elif opt.startswith("w"):                            # NAME+w16384: warm-start sample size
+            env["ABL_WARM"] = opt[1:]
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True,
                                timeout=float(os.environ.get("ABL_TIMEOUT", 90)))
