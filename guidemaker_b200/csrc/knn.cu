@@ -293,7 +293,7 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
         splits = (int)((want + grid_x - 1) / grid_x);
     }
     // warm start: worthwhile only when the table is much larger than the sample
-    int warm = g_tune_warm < 0 ? 4 * CHUNK : g_tune_warm;
+    int warm = g_tune_warm < 0 ? (use_tc ? 8 : 4) * CHUNK : g_tune_warm;   // measured: 8192 is best for K3b, 4096 for K3a
     warm = (warm + CHUNK - 1) / CHUNK;                       // in chunks
     if (n_chunks < 16 * warm || ix->n_u < (int64_t)warm * CHUNK) warm = 0;
     // K3b inherits the warm lists and scans only the chunks behind the sample; K3a rescans from chunk 0
@@ -359,11 +359,16 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
         rc = launch_hamming_tc(dim3((unsigned)(q_pad / tc_query_tile()), (unsigned)splits), st, a);
         if (rc) return rc;
         if (dbg_on) {
-            unsigned long long h[2];
+            unsigned long long h[56];
             GM_CUDA(cudaStreamSynchronize(st));
             GM_CUDA(cudaMemcpy(h, d_dbg, sizeof h, cudaMemcpyDeviceToHost));
-            fprintf(stderr, "[tc_dbg] candidate events %llu (%.2f per query), list inserts %llu (%.2f per query), grid %u x %d\n", h[0],
-                    (double)h[0] / (double)q, h[1], (double)h[1] / (double)q, (unsigned)(q_pad / tc_query_tile()), splits);
+            fprintf(stderr, "[tc_dbg] candidate events %llu (%.2f per query), list inserts %llu (%.2f per query), grid %u x %d; "
+                    "epilogue warps: %.1f %% of their time behind a full candidate queue (%llu stalls)\n", h[0],
+                    (double)h[0] / (double)q, h[1], (double)h[1] / (double)q, (unsigned)(q_pad / tc_query_tile()), splits,
+                    h[4] ? 100.0 * (double)h[2] / (double)h[4] : 0.0, h[3]);
+            fprintf(stderr, "[tc_dbg] cycles per tile over successive 256-tile windows of CTA 200:");
+            for (int w = 1; w < 48 && h[8 + w]; w++) fprintf(stderr, " %.0f", (double)(h[8 + w] - h[8 + w - 1]) / 256.0);
+            fprintf(stderr, "\n");
         }
     } else if (R == 8) launch_scan<8>(ix->metric, dim3((unsigned)tiles, (unsigned)splits), st, a);
     else launch_scan<4>(ix->metric, dim3((unsigned)tiles, (unsigned)splits), st, a);

@@ -45,7 +45,8 @@ namespace gm {
 
 // Timing-only ablations (tools/tc_ablate.py; results are wrong by construction): 1 = epilogue skips the TMEM loads,
 // 2 = producers skip the one-hot expansion, 4 = issuers skip the MMAs (commits only), 8 = candidate path disabled,
-// 16 = producers skip the proxy fence, 32 = producers do not wait for the stage to be released.
+// 16 = producers skip the proxy fence, 32 = producers do not wait for the stage to be released,
+// 128 = candidate warps pop events but do not serve them, 256 = one MMA K step fewer per tile.
 #ifndef GM_TC_ABL
 #define GM_TC_ABL 0
 #endif
@@ -62,7 +63,11 @@ static constexpr int TC_MMA_WARPS = 2 * TC_SETS;                   // (set, buff
 static constexpr int TC_CAND_WARP0 = TC_MMA_WARP + TC_MMA_WARPS;
 static constexpr int TC_CAND_WARPS = 4;                            // one per TMEM lane quadrant
 static constexpr int TC_THREADS = 32 * (TC_CAND_WARP0 + TC_CAND_WARPS);
-static constexpr int TC_QN = 32;           // entries per candidate queue (power of two)
+static constexpr int TC_QN = 64;           // entries per candidate queue (power of two)
+#ifndef GM_TC_IDLE_NS
+#define GM_TC_IDLE_NS 2000
+#endif
+static constexpr unsigned TC_IDLE_NS = GM_TC_IDLE_NS;   // idle candidate warps poll their queues this often
 static_assert(TC_SETS * 2 * TC_N == 512, "accumulator buffers must tile the 512 TMEM columns");
 static_assert(TC_THREADS <= 1024 && TC_EPI_WARPS * 32 == TC_QT, "one epilogue thread per query in the prologue");
 static constexpr uint32_t TC_FLAGS = 0x08200820u;   // bit 5 / bit 11 of both 16-bit halves of a packed register
@@ -153,6 +158,11 @@ __device__ __forceinline__ uint4 onehot_chunk(uint32_t eA, uint32_t eC, uint32_t
     return make_uint4((eA >> j) & 0x01010101u, (eC >> j) & 0x01010101u, (eG >> j) & 0x01010101u, (eT >> j) & 0x01010101u);
 }
 
+// a spin loop outlived ~10 s: fail the launch instead of hanging the GPU (1 = issue order, 2 = candidate queue)
+__device__ __noinline__ void tc_watchdog(int what) {
+    printf("libgm_b200: K3b watchdog %d fired (block %d,%d thread %d)\n", what, blockIdx.x, blockIdx.y, threadIdx.x);
+    __trap();
+}
 __device__ __forceinline__ uint32_t ld_vol(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
 __device__ __forceinline__ void st_vol(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
 
@@ -179,7 +189,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t b_full[TC_STAGES], b_empty[TC_STAGES], acc_full[TC_SETS][2], acc_empty[TC_SETS][2];
     __shared__ uint32_t s_tmem, s_done, s_issued[TC_SETS];
-    __shared__ uint32_t q_head[TC_EPI_WARPS], q_tail[TC_EPI_WARPS];       // candidate queues: consumer / producer cursor
+    __shared__ uint32_t q_head[TC_EPI_WARPS];                             // candidate queues: the consumers' cursors
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = a.L;
@@ -208,7 +218,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
         s_done = 0;
         for (int q = 0; q < TC_SETS; q++) s_issued[q] = 0;
     }
-    if (tid < TC_EPI_WARPS) { q_head[tid] = 0; q_tail[tid] = 0; }
+    if (tid < TC_EPI_WARPS) q_head[tid] = 0;
+    for (int i = tid; i < TC_EPI_WARPS * TC_QN; i += TC_THREADS) sQueue[i] = make_uint2(0u, 0u);   // generation 0 = nothing yet
     if (warp == TC_MMA_WARP) tc_alloc(&s_tmem, 512);
 
     // ---- per query: permuted planes, list, key bound ---------------------------------------------------------------
@@ -218,7 +229,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
     if (tid < TC_QT) {
         const int64_t qi = qbase + tid;               // < q_pad by construction
         const uint2 p = a.qplanes[qi];
-        sQ[tid] = make_uint2(tc_permute_bits(p.x), tc_permute_bits(p.y));
+        const int qslot = ((tid >> 8) * 128 + (tid & 127)) * 2 + ((tid >> 7) & 1);    // the two queries of a row are adjacent
+        sQ[qslot] = make_uint2(tc_permute_bits(p.x), tc_permute_bits(p.y));
         uint32_t bound = KEY_EMPTY;
         uint32_t *lst = s_lists + tid;
         if (a.warm) {
@@ -234,7 +246,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
         } else {
             for (int j = 0; j < a.k; j++) lst[j * TC_QT] = KEY_EMPTY;
         }
-        sBound[tid] = qi < a.q ? bound : 0u;          // padding queries never match
+        sBound[qslot] = qi < a.q ? bound : 0u;        // padding queries never match
     }
     __syncthreads();
     // ---- A tiles: set s, row r = query (256 s + r) * 1 + query (256 s + 128 + r) * 64 ------------------------------
@@ -243,8 +255,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
         uint32_t e[2][4], tau[2];
 #pragma unroll
         for (int s = 0; s < 2; s++) {
-            const uint2 p = sQ[set * 256 + s * 128 + row];
-            tau[s] = sBound[set * 256 + s * 128 + row] >> IDX_BITS;
+            const uint2 p = sQ[(set * 128 + row) * 2 + s];
+            tau[s] = sBound[(set * 128 + row) * 2 + s] >> IDX_BITS;
             e[s][0] = ~(p.x | p.y) & lmask; e[s][1] = p.x & ~p.y; e[s][2] = p.y & ~p.x; e[s][3] = p.x & p.y;
         }
         uint8_t *myA = sA + (size_t)set * a_bytes;
@@ -273,10 +285,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
         const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)set * (2 * TC_N) + (uint32_t)par * TC_N;
         uint2 *queue = sQueue + warp * TC_QN;
         uint32_t tail = 0;
+        uint32_t stall_clk = 0, n_stalls = 0;                       // lane 0: time (units of 64 cycles) spent behind a full candidate queue
+        const long long t_begin = clock64();
         uint32_t r[32];
         for (int i = par; i < n_tiles; i += 2) {
             mbar_wait(&acc_full[set][par], (uint32_t)((i >> 1) & 1));
             tc_fence_after();
+            if (a.dbg && (i & 255) == 0 && (i >> 8) < 48 && blockIdx.x == 200 && warp == 0 && lane == 0)     // GM_TC_DEBUG: tile-rate profile of one CTA
+                a.dbg[8 + (i >> 8)] = (unsigned long long)(clock64() - t_begin);
             uint32_t f[4];
 #if GM_TC_ABL & 1
             f[0] = f[1] = f[2] = f[3] = 0u;
@@ -295,22 +311,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[set][par]);       // buffer released before any candidate work
-            const uint32_t t0 = (uint32_t)(tile0 + i) * TC_N;
+            // One vote says whether anything in the tile is flagged (usually not); then one event per flagged chunk.
+            // (One event per tile with the union of the rows was measured slower: the candidate warp's extra shared-memory
+            // reads cost more than the pushes they save -- shared-memory cycles are what this kernel runs out of.)
+            if (__any_sync(0xFFFFFFFFu, ((f[0] | f[1] | f[2] | f[3]) & TC_FLAGS) != 0) && !(GM_TC_ABL & 8)) {
+                const uint32_t t0 = (uint32_t)(tile0 + i) * TC_N;
 #pragma unroll
-            for (int h = 0; h < 4; h++) {
-                const uint32_t fl = __ballot_sync(0xFFFFFFFFu, (f[h] & TC_FLAGS) != 0);
-                if (fl && !(GM_TC_ABL & 8)) {
+                for (int h = 0; h < 4; h++) {
+                    const uint32_t fl = __ballot_sync(0xFFFFFFFFu, (f[h] & TC_FLAGS) != 0);
+                    if (fl == 0) continue;
                     if (lane == 0) {
                         if (tail - ld_vol(&q_head[warp]) >= (uint32_t)TC_QN) {      // queue full: wait for the candidate warp
                             const long long w0 = clock64();
                             while (tail - ld_vol(&q_head[warp]) >= (uint32_t)TC_QN) {
-                                __nanosleep(64);
-                                if (clock64() - w0 > 20000000000LL) { printf("libgm_b200: candidate queue watchdog fired\n"); __trap(); }
+                                __nanosleep(256);
+                                if (clock64() - w0 > 20000000000LL) tc_watchdog(2);
                             }
+                            stall_clk += (uint32_t)((clock64() - w0) >> 6);
+                            n_stalls++;
                         }
-                        queue[tail & (TC_QN - 1)] = make_uint2(t0 + (uint32_t)h * 32u, fl);
-                        __threadfence_block();
-                        st_vol(&q_tail[warp], tail + 1);
+                        // One 8-byte store publishes the event: bit 31 of the first word is a generation tag that flips on
+                        // every lap of the ring, so the consumer polls the slot itself and no fence (MEMBAR, ~200 cycles
+                        // on this warp's chain) or tail pointer is needed.  (Target indices are < 2^27.)
+                        const uint32_t gen = ((tail / TC_QN) & 1u) ^ 1u;
+                        *reinterpret_cast<volatile unsigned long long *>(&queue[tail & (TC_QN - 1)]) =
+                            (unsigned long long)((t0 + (uint32_t)h * 32u) | (gen << 31)) | ((unsigned long long)fl << 32);
                     }
                     tail++;
                 }
@@ -318,6 +343,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
         }
         __syncwarp();
         if (lane == 0) { __threadfence_block(); atomicAdd(&s_done, 1u); }
+        if (a.dbg && lane == 0) {
+            atomicAdd(&a.dbg[2], (unsigned long long)stall_clk << 6);
+            atomicAdd(&a.dbg[3], (unsigned long long)n_stalls);
+            atomicAdd(&a.dbg[4], (unsigned long long)(clock64() - t_begin));
+        }
     } else if (warp < TC_MMA_WARP) {
         // ================= producers: planes -> one-hot B tile (one target per thread, group g takes tiles g, g+2, ..) ===
         const int pw = warp - TC_PROD_WARP0, grp = pw >> 2, p = (pw & 3) * 32 + lane;
@@ -369,15 +399,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
             // strictly closer than the k-th best" exact under the (distance, index) order.
             if (ld_vol(&s_issued[q]) != (uint32_t)i) {
                 const long long w0 = clock64();
-                while (ld_vol(&s_issued[q]) != (uint32_t)i)
-                    if (clock64() - w0 > 20000000000LL) { printf("libgm_b200: issue-order watchdog fired\n"); __trap(); }
+                while (ld_vol(&s_issued[q]) != (uint32_t)i) {
+                    __nanosleep(20);                                // (a tight loop would eat shared-memory cycles)
+                    if (clock64() - w0 > 20000000000LL) tc_watchdog(1);
+                }
             }
             tc_fence_after();
             const uint64_t db = db0 + (uint64_t)((uint32_t)s * b_stage);
             const uint32_t bar_e = bar_bempty_u + (uint32_t)(s * 8);
             if (leader) {
 #pragma unroll
-                for (int ks = 0; ks < ((GM_TC_ABL & 4) ? 0 : n_ks); ks++)
+                for (int ks = 0; ks < ((GM_TC_ABL & 4) ? 0 : (GM_TC_ABL & 256) ? n_ks - 1 : n_ks); ks++)
                     tc_mma_i8(d, da + (uint64_t)((uint32_t)ks * a_ks), db + (uint64_t)((uint32_t)ks * b_ks), idesc, ks > 0 ? 1u : 0u);
                 __threadfence_block();
                 st_vol(&s_issued[q], (uint32_t)i + 1u);             // the set's other issuer may go ahead
@@ -389,7 +421,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
     } else {
         // ================= candidate warps: warp c owns the queries of TMEM quadrant c of both sets ====================
         const int c = warp - TC_CAND_WARP0;
-        uint32_t head[4] = {0u, 0u, 0u, 0u};
         unsigned long long n_events = 0, n_inserts = 0;
         // one event = (first target of a 32-target chunk, mask of flagged rows); `set` selects the A operand
         auto serve = [&](const uint2 ev, const uint2 tp, const int set) {
@@ -399,61 +430,71 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
             while (fl) {
                 const int row = c * 32 + (__ffs(fl) - 1);
                 fl &= fl - 1;
+                // both queries of the row at once: one 16-byte and one 8-byte shared-memory read, two ballots
+                const uint4 qq = reinterpret_cast<const uint4 *>(sQ)[set * 128 + row];
+                const uint2 bb = reinterpret_cast<const uint2 *>(sBound)[set * 128 + row];
+                const uint32_t key[2] = {((uint32_t)hamming_planes(qq.x, qq.y, tp.x, tp.y) << IDX_BITS) | kpart,
+                                         ((uint32_t)hamming_planes(qq.z, qq.w, tp.x, tp.y) << IDX_BITS) | kpart};
+                const uint32_t hit[2] = {__ballot_sync(0xFFFFFFFFu, valid && key[0] < bb.x),
+                                         __ballot_sync(0xFFFFFFFFu, valid && key[1] < bb.y)};
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
-                    const int qx = set * 256 + e * 128 + row;
-                    const uint2 qp = sQ[qx];
-                    uint32_t bound = sBound[qx];
-                    const uint32_t key = ((uint32_t)hamming_planes(qp.x, qp.y, tp.x, tp.y) << IDX_BITS) | kpart;
-                    uint32_t hits = __ballot_sync(0xFFFFFFFFu, valid && key < bound);
+                    uint32_t hits = hit[e];
                     if (hits == 0) continue;
-                    const uint32_t bound0 = bound;
+                    const uint32_t bound0 = e ? bb.y : bb.x;
+                    uint32_t bound = bound0;
+                    uint32_t *lst = s_lists + set * 256 + e * 128 + row;
                     while (hits) {                                  // ascending target index
                         const int i = __ffs(hits) - 1;
                         hits &= hits - 1;
-                        const uint32_t ki = __shfl_sync(0xFFFFFFFFu, key, i);
+                        const uint32_t ki = __shfl_sync(0xFFFFFFFFu, key[e], i);
                         if (ki < bound) {
                             uint32_t w = 0;
-                            if (lane == 0) w = list_insert_smem(s_lists + qx, a.k, ki);
+                            if (lane == 0) w = list_insert_smem(lst, a.k, ki);
                             w = __shfl_sync(0xFFFFFFFFu, w, 0);
                             bound = min(bound, w);
                             n_inserts++;
                         }
                     }
                     if (bound != bound0 && lane == 0) {
-                        sBound[qx] = bound;
-                        if ((bound >> IDX_BITS) != (bound0 >> IDX_BITS)) {       // tighten the bias byte; later MMAs pick it up
+                        sBound[(set * 128 + row) * 2 + e] = bound;
+                        // tighten the bias byte; later MMAs pick it up.  No proxy fence: the byte only has to reach the
+                        // tensor core eventually (measured: the fence changes nothing)
+                        if ((bound >> IDX_BITS) != (bound0 >> IDX_BITS))
                             sA[(size_t)set * a_bytes + (size_t)nd * (TC_M * 16) + (size_t)row * 16 + e] =
                                 (uint8_t)(31 - L + (int)(bound >> IDX_BITS));
-                            fence_async_smem();
-                        }
                     }
                     __syncwarp();
                 }
             }
         };
+        uint32_t head[4] = {0u, 0u, 0u, 0u};
         for (;;) {
             const uint32_t done = ld_vol(&s_done);                  // read BEFORE the scan: done + empty queues = finished
-            // take at most one event from each of the four queues (x = (set, buffer)) and issue their loads together
+            // poll the next slot of each of the four queues (x = (set, buffer)); a slot is valid when its generation tag
+            // matches the lap the cursor is on
+            uint2 ev[4], tp[4];
             bool have[4];
             bool any = false;
 #pragma unroll
             for (int x = 0; x < 4; x++) {
-                have[x] = head[x] != ld_vol(&q_tail[(x >> 1) * 8 + (x & 1) * 4 + c]);
+                const int qid = (x >> 1) * 8 + (x & 1) * 4 + c;
+                const unsigned long long w = *reinterpret_cast<const volatile unsigned long long *>(&sQueue[qid * TC_QN + (head[x] & (TC_QN - 1))]);
+                ev[x] = make_uint2((uint32_t)w, (uint32_t)(w >> 32));
+                have[x] = (ev[x].x >> 31) == (((head[x] / TC_QN) & 1u) ^ 1u) && ev[x].y != 0u;
                 any |= have[x];
             }
             if (!any) {
                 if (done == (uint32_t)TC_EPI_WARPS) break;
-                __nanosleep(32);
+                // every poll costs shared-memory cycles the tensor core needs for its operands: sleep generously
+                __nanosleep(TC_IDLE_NS);
                 continue;
             }
-            __threadfence_block();
-            uint2 ev[4], tp[4];
 #pragma unroll
             for (int x = 0; x < 4; x++)
                 if (have[x]) {
-                    ev[x] = sQueue[((x >> 1) * 8 + (x & 1) * 4 + c) * TC_QN + (head[x] & (TC_QN - 1))];
-                    tp[x] = a.tperm[(size_t)ev[x].x + lane];
+                    ev[x].x &= 0x7FFFFFFFu;
+                    tp[x] = a.tperm[(size_t)ev[x].x + lane];          // the loads of all taken events are in flight together
                     head[x]++;
                 }
             __syncwarp();
@@ -464,7 +505,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
             }
 #pragma unroll
             for (int x = 0; x < 4; x++)
-                if (have[x]) { serve(ev[x], tp[x], x >> 1); n_events++; }
+                if (have[x]) { if (!(GM_TC_ABL & 128)) serve(ev[x], tp[x], x >> 1); n_events++; }
         }
         if (a.dbg && lane == 0) { atomicAdd(&a.dbg[0], n_events); atomicAdd(&a.dbg[1], n_inserts); }
     }
