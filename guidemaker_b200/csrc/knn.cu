@@ -285,7 +285,23 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
 
     // target splits: enough CTAs for >= ~16 per SM so the last wave is a small fraction
     int splits = g_tune_splits;
-    if (splits <= 0) {
+    // K3b runs one CTA per SM, so a launch of T query tiles takes ceil(T / SMs) waves and the last one may be nearly
+    // empty (T = 335 on each of 8 GPUs for the 6.3 Mb config: 2.26 waves of work in 3).  Two-tier launch: the largest
+    // multiple of the SM count runs unsplit, the remaining `tail_tiles` are cut into `tail_splits` target ranges so they
+    // fill ONE short wave (a split restarts with loose bounds, which costs ~16 % of an unsplit CTA, measured).
+    int tail_tiles = 0, tail_splits = 1;
+    if (use_tc && splits <= 0) {
+        const int sms = device_sm_count();
+        const int64_t grid_x = q_pad / tc_query_tile();
+        const int rem = (int)(grid_x % sms);
+        if (grid_x > sms && rem > 0 && sms / rem >= 2) {
+            tail_tiles = rem;
+            tail_splits = sms / rem > 8 ? 8 : sms / rem;
+        }
+    }
+    if (tail_tiles) {
+        splits = 1;
+    } else if (splits <= 0) {
         // K3a: >= 16 CTAs per SM.  K3b: one resident CTA per SM and every split restarts with the loose warm-start
         // thresholds (measured ~0.6 ms of SM time per extra CTA), so it only splits to reach ~2 CTAs per SM
         const int64_t grid_x = use_tc ? q_pad / tc_query_tile() : tiles;
@@ -305,9 +321,17 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     if (splits < 1) splits = 1;
     int cps = (scan_chunks + splits - 1) / splits;
     splits = (scan_chunks + cps - 1) / cps;
+    int tail_cps = 0;
+    if (tail_tiles) {
+        if (tail_splits > scan_chunks) tail_splits = scan_chunks;
+        tail_cps = (scan_chunks + tail_splits - 1) / tail_splits;
+        tail_splits = (scan_chunks + tail_cps - 1) / tail_cps;
+        if (tail_splits < 2) { tail_tiles = 0; tail_splits = 1; }
+    }
+    const int list_splits = tail_tiles ? tail_splits : splits;          // split lists per query that memset / merge see
 
     const size_t qp_bytes = (size_t)q_pad * sizeof(uint2);
-    const size_t list_bytes = (size_t)splits * q_pad * k * sizeof(uint32_t);
+    const size_t list_bytes = (size_t)list_splits * q_pad * k * sizeof(uint32_t);
     const size_t warm_bytes = warm ? (size_t)q_pad * k * sizeof(uint32_t) : 0;
     int rc = ensure_ws(ix, qp_bytes + list_bytes + warm_bytes, st);
     if (rc) return rc;
@@ -323,6 +347,7 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     a.tplanes = ix->planes;
     a.tperm = ix->planes_perm;
     a.first_chunk = 0;
+    a.tile_offset = 0;
     a.n_u = ix->n_u;
     a.qplanes = qplanes;
     a.q = q;
@@ -356,15 +381,22 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     a.warm = wlists;
     if (use_tc) {
         a.dbg = dbg_on ? d_dbg : nullptr;
-        rc = launch_hamming_tc(dim3((unsigned)(q_pad / tc_query_tile()), (unsigned)splits), st, a);
+        const unsigned grid_x = (unsigned)(q_pad / tc_query_tile());
+        rc = launch_hamming_tc(dim3(grid_x - (unsigned)tail_tiles, (unsigned)splits), st, a);
         if (rc) return rc;
+        if (tail_tiles) {                                           // the last query tiles, split to fill one short wave
+            a.tile_offset = (int)grid_x - tail_tiles;
+            a.chunks_per_split = tail_cps;
+            rc = launch_hamming_tc(dim3((unsigned)tail_tiles, (unsigned)tail_splits), st, a);
+            if (rc) return rc;
+        }
         if (dbg_on) {
             unsigned long long h[56];
             GM_CUDA(cudaStreamSynchronize(st));
             GM_CUDA(cudaMemcpy(h, d_dbg, sizeof h, cudaMemcpyDeviceToHost));
             fprintf(stderr, "[tc_dbg] candidate events %llu (%.2f per query), list inserts %llu (%.2f per query), grid %u x %d; "
                     "epilogue warps: %.1f %% of their time behind a full candidate queue (%llu stalls)\n", h[0],
-                    (double)h[0] / (double)q, h[1], (double)h[1] / (double)q, (unsigned)(q_pad / tc_query_tile()), splits,
+                    (double)h[0] / (double)q, h[1], (double)h[1] / (double)q, (unsigned)(q_pad / tc_query_tile()), list_splits,
                     h[4] ? 100.0 * (double)h[2] / (double)h[4] : 0.0, h[3]);
             fprintf(stderr, "[tc_dbg] cycles per tile over successive 256-tile windows of CTA 200:");
             for (int w = 1; w < 48 && h[8 + w]; w++) fprintf(stderr, " %.0f", (double)(h[8 + w] - h[8 + w - 1]) / 256.0);
@@ -375,7 +407,7 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     pairs += (double)q * ((double)ix->n_u - (double)first_chunk * CHUNK);
     prof_end(slot, st, pairs);
 
-    knn_merge_kernel<<<(unsigned)((q + 127) / 128), 128, 0, st>>>(lists, splits, q, q_pad, k, d_idx, d_dist, dist_only);
+    knn_merge_kernel<<<(unsigned)((q + 127) / 128), 128, 0, st>>>(lists, list_splits, q, q_pad, k, d_idx, d_dist, dist_only);
     count_launch();
     GM_CUDA(cudaGetLastError());
     return GM_OK;

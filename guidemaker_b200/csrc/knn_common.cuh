@@ -54,6 +54,7 @@ struct ScanArgs {
     const uint2 *tplanes;
     const uint2 *tperm;       // K3b: bit-permuted planes of the same table
     int first_chunk;          // K3b: the scan starts here (behind the warm sample, whose lists split 0 inherits)
+    int tile_offset;          // K3b: blockIdx.x + tile_offset = query tile (the tail launch covers the last tiles)
     int n_chunks;             // chunks to cover (ceil(n_scan / CHUNK))
     int chunks_per_split;
     int64_t n_u;              // targets beyond this index are padding

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
     const int c1 = min(c0 + a.chunks_per_split, a.n_chunks);
     if (c0 >= c1) return;
     const int tile0 = c0 * (CHUNK / TC_N), n_tiles = (c1 - c0) * (CHUNK / TC_N);
-    const int64_t qbase = (int64_t)blockIdx.x * TC_QT;
+    const int64_t qbase = ((int64_t)blockIdx.x + a.tile_offset) * TC_QT;
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(&b_full[s], 4); mbar_init(&b_empty[s], TC_SETS); }
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
         for (int i = par; i < n_tiles; i += 2) {
             mbar_wait(&acc_full[set][par], (uint32_t)((i >> 1) & 1));
             tc_fence_after();
-            if (a.dbg && (i & 255) == 0 && (i >> 8) < 48 && blockIdx.x == 200 && warp == 0 && lane == 0)     // GM_TC_DEBUG: tile-rate profile of one CTA
+            if (a.dbg && (i & 255) == 0 && (i >> 8) < 48 && blockIdx.x + a.tile_offset == 200 && warp == 0 && lane == 0)     // GM_TC_DEBUG: tile-rate profile of one CTA
                 a.dbg[8 + (i >> 8)] = (unsigned long long)(clock64() - t_begin);
             uint32_t f[4];
 #if GM_TC_ABL & 1
