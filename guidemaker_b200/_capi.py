@@ -35,6 +35,8 @@ _SIGS = {
     "gm_scan_free": [_vp],
     "gm_seed_dedup": [_vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp],
     "gm_first_occurrence": [_vp, ctypes.c_int64, _vp],
+    "gm_restriction_scan": [_vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp],
+    "gm_restriction_scan_dev": [_vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp],
     "gm_index_create": [_vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)],
     "gm_index_create_dev": [_vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp), _vp],
     "gm_index_info": [_vp, _c_i64p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)],
@@ -147,6 +149,29 @@ def first_occurrence(keys: np.ndarray) -> np.ndarray:
     out = np.zeros(len(keys), np.int64)
     _check(load_library().gm_first_occurrence(_p(keys), len(keys), _p(out)), "gm_first_occurrence")
     return out
+
+
+# IUPAC letter -> accepted bases (bit 0 = A, 1 = C, 2 = G, 3 = T); X and N accept everything (core.py:1107-1110)
+IUPAC_SETS = {"A": 1, "C": 2, "G": 4, "T": 8, "M": 3, "R": 5, "W": 9, "S": 6, "Y": 10, "K": 12, "V": 7, "H": 11, "D": 13,
+              "B": 14, "X": 15, "N": 15}
+MAX_MOTIF = 32
+
+
+def restriction_scan(guides: np.ndarray, L: int, motifs) -> np.ndarray:
+    """bool[n]: guide contains one of the IUPAC motifs (upper-case strings) at some offset (K6)."""
+    init()
+    guides = np.ascontiguousarray(guides, np.uint64)
+    motifs = list(motifs)
+    sets = np.zeros((max(len(motifs), 1), MAX_MOTIF), np.uint8)
+    lens = np.zeros(max(len(motifs), 1), np.int32)
+    for t, m in enumerate(motifs):
+        lens[t] = len(m)
+        for j, ch in enumerate(m[:MAX_MOTIF]):
+            sets[t, j] = IUPAC_SETS[ch]
+    out = np.zeros(len(guides), np.uint8)
+    _check(load_library().gm_restriction_scan(_p(guides), len(guides), int(L), _p(sets), _p(lens), len(motifs), _p(out)),
+           "gm_restriction_scan")
+    return out.view(np.bool_)
 
 
 # ---- K3/K4/K5 ---------------------------------------------------------------------------------------

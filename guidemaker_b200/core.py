@@ -243,16 +243,19 @@ class TargetProcessor:
 
     # ---- reference API -------------------------------------------------------------------------------
     def check_restriction_enzymes(self, restriction_enzyme_list: list = []) -> None:
-        """Flag guides containing a restriction site or its reverse complement (core.py:354-377)."""
-        element_to_exclude = []
+        """Flag guides containing a restriction site or its reverse complement (core.py:354-377).
+
+        The reference expands every IUPAC site into all concrete strings and regex-searches their alternation;
+        the same predicate is evaluated on the packed guides by the K6 kernel (``gm_restriction_scan``)."""
+        motifs = []
         for record in set(restriction_enzyme_list):
             for letter in record.upper():
                 assert letter in _IUPAC_LETTERS
-            element_to_exclude.append(extend_ambiguous_dna(record.upper()))
-            element_to_exclude.append(extend_ambiguous_dna(_reverse_complement(record.upper())))
-        element_to_exclude = sum(element_to_exclude, [])
-        if len(element_to_exclude) > 0:
-            self.targets['hasrestrictionsite'] = self.targets['target'].str.contains('|'.join(element_to_exclude))
+            motifs.append(record.upper())
+            motifs.append(_reverse_complement(record.upper()))
+        if len(motifs) > 0:
+            guides, L = self._packed()
+            self.targets['hasrestrictionsite'] = _capi.restriction_scan(guides, L, motifs)
         else:
             self.targets['hasrestrictionsite'] = False
 

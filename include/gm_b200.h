@@ -10,6 +10,7 @@
  *                        check_target                                   core.py:142-246 (call sites :154,:182,:207,:234)
  *   gm_seed_dedup        Series.duplicated() over the seed strings      core.py:402-416
  *   gm_first_occurrence  list(set(targets))  (made deterministic: first-occurrence order) core.py:446
+ *   gm_restriction_scan  targets.str.contains('|'.join(expanded sites))  core.py:354-377 (call site :375)
  *   gm_index_create      nmslib.init + addDataPointBatch + createIndex  core.py:451-457, :461-467
  *   gm_knn               index.knnQueryBatch(queries, k=knum)           core.py:502-503
  *   gm_min_dist          index.knnQueryBatch(binseq, k=2) -> i[1][0]    core.py:603-606
@@ -81,6 +82,17 @@ int gm_seed_dedup(const uint64_t *guide2bit, int64_t n, int L, int lsr, int five
 /* first_row[i] = smallest row whose key equals keys[i] (distinct guides in first-occurrence
  * order are the rows with first_row[i] == i). n < 2^31. */
 int gm_first_occurrence(const uint64_t *keys, int64_t n, int64_t *first_row);
+
+/* ---- K6: restriction-site flag ------------------------------------------------------------------
+ * has_site[i] = 1 iff some motif occurs in guide i at any offset.  A motif is a string of letter sets:
+ * motif_sets[t * 32 + j] = accepted bases of position j of motif t (bit 0 = A, 1 = C, 2 = G, 3 = T; 1..15),
+ * motif_len[t] its length (0 = the empty pattern, which matches every guide as the reference's regex
+ * does; a motif longer than L never matches).  The caller passes each enzyme site AND its reverse
+ * complement, as core.py:367-370 does.  n_motifs = 0 clears the flags. */
+int gm_restriction_scan(const uint64_t *guide2bit, int64_t n, int L, const uint8_t *motif_sets,
+                        const int32_t *motif_len, int n_motifs, uint8_t *has_site);
+int gm_restriction_scan_dev(const uint64_t *d_guide2bit, int64_t n, int L, const uint8_t *motif_sets,
+                            const int32_t *motif_len, int n_motifs, uint8_t *d_has_site, void *stream);
 
 /* ---- K3/K4/K5: exact brute-force kNN index -----------------------------------------------------
  * The index is the table of distinct guides resident in HBM (bit-plane layout).

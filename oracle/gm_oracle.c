@@ -295,3 +295,46 @@ int gmo_num_threads(void)
     return 1;
 #endif
 }
+
+/* ---- restriction-site flag (core.py:354-377) -------------------------------------------------
+ * The reference expands every site and its reverse complement into all concrete strings
+ * (extend_ambiguous_dna, core.py:1093-1124) and flags a guide when
+ * targets.str.contains('|'.join(expansions)) -- a plain substring search for any expansion.
+ * Restated directly: guide i is flagged iff for some motif t and offset o every motif position j
+ * accepts base o + j of the guide.  iupac[t * 32 + j] holds the IUPAC LETTER of position j; the
+ * accepted bases come from the table of core.py:1103-1120 (X and N accept all four).  A motif of
+ * length 0 is the empty pattern and matches every guide, as the regex does. */
+static int gmo_letter_set(char c)
+{
+    switch (c) {
+    case 'A': return 1; case 'C': return 2; case 'G': return 4; case 'T': return 8;
+    case 'M': return 1 | 2; case 'R': return 1 | 4; case 'W': return 1 | 8; case 'S': return 2 | 4;
+    case 'Y': return 2 | 8; case 'K': return 4 | 8; case 'V': return 1 | 2 | 4; case 'H': return 1 | 2 | 8;
+    case 'D': return 1 | 4 | 8; case 'B': return 2 | 4 | 8; case 'X': case 'N': return 15;
+    default: return 0;
+    }
+}
+
+int gmo_restriction(const uint64_t *guides, int64_t n, int L, const char *iupac, const int32_t *motif_len, int n_motifs,
+                    uint8_t *has_site)
+{
+    for (int t = 0; t < n_motifs; t++)
+        for (int j = 0; j < motif_len[t] && j < 32; j++)
+            if (!gmo_letter_set(iupac[t * 32 + j])) return -2;
+    for (int64_t i = 0; i < n; i++) {
+        int hit = 0;
+        for (int t = 0; t < n_motifs && !hit; t++) {
+            const int len = motif_len[t];
+            for (int o = 0; o + len <= L && !hit; o++) {
+                int ok = 1;
+                for (int j = 0; j < len && ok; j++) {
+                    const int base = (int)((guides[i] >> (2 * (o + j))) & 3u);
+                    ok = (gmo_letter_set(iupac[t * 32 + j]) >> base) & 1;
+                }
+                hit = ok;
+            }
+        }
+        has_site[i] = (uint8_t)hit;
+    }
+    return 0;
+}

@@ -66,7 +66,10 @@ def lib() -> ctypes.CDLL:
                               ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.gmo_min_dist.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_void_p, ctypes.c_int]
-        for f in (L.gmo_pam_scan, L.gmo_seed_dedup, L.gmo_first_occurrence, L.gmo_knn, L.gmo_min_dist, L.gmo_num_threads):
+        L.gmo_restriction.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_void_p]
+        for f in (L.gmo_pam_scan, L.gmo_seed_dedup, L.gmo_first_occurrence, L.gmo_knn, L.gmo_min_dist, L.gmo_num_threads,
+                  L.gmo_restriction):
             f.restype = ctypes.c_int
         del u8p, u16p, u32p, u64p, i32p
         _LIB = L
@@ -164,6 +167,24 @@ def c_min_dist(targets, queries, L: int, metric: int, threads: int = 0):
     return dist
 
 
+def c_restriction(guides, L: int, motifs) -> np.ndarray:
+    """bool[n]: guide contains one of the IUPAC motifs (the caller passes sites AND reverse complements)."""
+    guides = np.ascontiguousarray(guides, np.uint64)
+    motifs = list(motifs)
+    if any(len(m) > 32 for m in motifs):
+        motifs = [m for m in motifs if len(m) <= 32]          # longer than any guide: can never occur
+    buf = bytearray(32 * max(len(motifs), 1))
+    lens = np.zeros(max(len(motifs), 1), np.int32)
+    for t, m in enumerate(motifs):
+        buf[32 * t: 32 * t + len(m)] = m.encode()
+        lens[t] = len(m)
+    out = np.zeros(len(guides), np.uint8)
+    rc = lib().gmo_restriction(_ptr(guides), len(guides), L, bytes(buf), _ptr(lens), len(motifs), _ptr(out))
+    if rc != 0:
+        raise ValueError(f"gmo_restriction rc={rc}")
+    return out.astype(bool)
+
+
 def num_threads() -> int:
     return lib().gmo_num_threads()
 
@@ -206,6 +227,22 @@ def py_find_targets(seq: str, pam: str, five_prime: bool, L: int):
                 rows.append((t, reverse_complement(m.group(0)), m.end(), m.end() + L, False, False,
                              reverse_complement(seq[m.start() - 3: m.start() + 27])))
     return rows
+
+
+def py_restriction(targets, enzymes) -> np.ndarray:
+    """check_restriction_enzymes, line by line (core.py:365-377): expand every site and its reverse complement
+    with itertools.product over the IUPAC table, join with '|', regex-search every target."""
+    import re
+    from itertools import product
+    element_to_exclude = []
+    for record in set(enzymes):
+        for rec in (record.upper(), reverse_complement(record.upper())):
+            element_to_exclude.append(["".join(i) for i in product(*[IUPAC[j] for j in rec])])
+    element_to_exclude = sum(element_to_exclude, [])
+    if not element_to_exclude:
+        return np.zeros(len(targets), bool)
+    pat = re.compile("|".join(element_to_exclude))
+    return np.array([pat.search(t) is not None for t in targets], dtype=bool)
 
 
 def py_seed(t: str, lsr: int, five_prime: bool) -> str:

@@ -257,6 +257,54 @@ def test_knn_tc_equals_popc_engine_at_scale(capi_mod):
     assert np.array_equal(b[0][rows], oi) and np.array_equal(b[1][rows], od)
 
 
+def test_knn_tc_tail_wave_launch(capi_mod):
+    """160 query tiles on 148 SMs: the 12 tiles behind the full wave run as a second launch cut into target splits
+    (knn.cu, two-tier launch).  Same bits as K3a, and as the oracle on a sample."""
+    capi = capi_mod
+    rng = np.random.default_rng(12)
+    t, _ = O.unique_first_order(rand_guides(rng, 150000, 20, n_base=140000))
+    q = rand_guides(rng, 160 * 512 - 77, 20)
+    ix = capi.Index(t, 20, 0)
+    capi.knn_tune(8, 0, -1)
+    capi.knn_engine(0)
+    a = ix.knn(q, 4)
+    capi.knn_engine(1)
+    b = ix.knn(q, 4)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    rows = np.concatenate([rng.integers(0, len(q), size=100), np.arange(len(q) - 100, len(q))])   # incl. the tail tiles
+    oi, od = O.c_knn(t, q[rows], 20, 0, 4)
+    assert np.array_equal(b[0][rows], oi) and np.array_equal(b[1][rows], od)
+    d1 = ix.min_dist(q[-5000:])
+    assert np.array_equal(d1, b[1][-5000:, 0])
+
+
+# ---- K6 ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L", [1, 7, 10, 20, 27])
+def test_restriction_scan_vs_oracle(capi_mod, L):
+    """IUPAC motif search on packed guides (check_restriction_enzymes, core.py:354-377) against the C oracle, and
+    against the literal regex restatement on a sample"""
+    capi = capi_mod
+    rng = np.random.default_rng(100 + L)
+    g = rand_guides(rng, 20011, L)
+    letters = list(O.IUPAC)
+    cases = [[], [""], ["A"], ["N"], ["GGTCTC", "NGGTAB"], ["NRAGCA"], ["ACGT" * 8], ["T" * L], ["N" * (L + 1)]]
+    for _ in range(12):
+        cases.append(["".join(rng.choice(letters, size=int(rng.integers(1, 9)))) for _ in range(int(rng.integers(1, 5)))])
+    cases.append(["".join(rng.choice(letters, size=int(rng.integers(2, 7)))) for _ in range(40)])     # > 64 motifs: two batches
+    for enz in cases:
+        motifs = []
+        for r in set(enz):
+            motifs += [r, O.reverse_complement(r)]
+        got = capi.restriction_scan(g, L, motifs)
+        assert np.array_equal(got, O.c_restriction(g, L, motifs)), enz
+        if sum(4 ** sum(c in "NX" for c in m) * 3 ** sum(c in "VHDB" for c in m) for m in motifs) < 5000:
+            sample = g[:400]
+            assert np.array_equal(got[:400], O.py_restriction([O.unpack(v, L) for v in sample], enz)), enz
+    assert len(capi.restriction_scan(g[:0], L, ["GAATTC"])) == 0
+    with pytest.raises(KeyError):
+        capi.restriction_scan(g, L, ["GAZTTC"])
+
+
 # ---- K4 ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("L", [10, 20, 23, 27])
 def test_knn_leven_vs_oracle(capi, L):

@@ -188,3 +188,46 @@ def test_c_dedup_and_knn_equal_python(seed):
         pi, pd_ = O.py_knn(useqs, seqs[:25], metric, k)
         assert idx.tolist() == pi and dist.tolist() == pd_
         assert O.c_min_dist(uniq, g[:25], L, metric).tolist() == [r[0] for r in pd_]
+
+
+# ---- restriction-site flag (core.py:354-377) ------------------------------------------------------------------------
+def test_restriction_flags_vs_reference_fixtures(carsonella, carsonella_ref, synthetic_ref):
+    """hasrestrictionsite as written by the reference's check_restriction_enzymes (tests/golden/make_golden.py:
+    Carsonella with ['NRAGCA'], the synthetic genome with ['GGTCTC', 'NGGTAB'])"""
+    def motifs(enz):
+        out = []
+        for r in set(enz):
+            out += [r.upper(), O.reverse_complement(r.upper())]
+        return out
+    n = 0
+    for name, (pam, five, L, lsr) in CASES.items():
+        key = name + "/hasrestrictionsite"
+        if key in carsonella_ref.files:
+            tgt = [t.decode() for t in carsonella_ref[name + "/target"]]
+            assert np.array_equal(O.c_restriction(O.pack_many(tgt), L, motifs(["NRAGCA"])), carsonella_ref[key]), name
+            assert np.array_equal(O.py_restriction(tgt, ["NRAGCA"]), carsonella_ref[key]), name
+            n += 1
+    r = synthetic_ref
+    for key in [k for k in r.files if k.endswith("/hasrestrictionsite")]:
+        name = key[: -len("/hasrestrictionsite")]
+        tgt = [t.decode() for t in r[name + "/target"]]
+        L = len(tgt[0])
+        ref = r[key]
+        if ref.dtype != bool or not ref.any():
+            continue                                   # cases run without restriction enzymes
+        assert np.array_equal(O.c_restriction(O.pack_many(tgt), L, motifs(["GGTCTC", "NGGTAB"])), ref), name
+        n += 1
+    assert n >= 2
+
+
+def test_restriction_c_equals_literal_restatement():
+    rng = np.random.default_rng(5)
+    for L in (8, 20, 27):
+        seqs = ["".join(rng.choice(list("ACGT"), L)) for _ in range(1500)]
+        g = O.pack_many(seqs)
+        for enz in (["NRAGCA"], ["GGTCTC", "NGGTAB"], ["A"], [""], ["ACGTACGTACGTACGTACGTACGTACGTACGT"], [], ["TTTV", "GAATTC", "CCWGG"],
+                    ["RYKM", "SWBD"], ["ggtctc"]):
+            motifs = []
+            for r in set(enz):
+                motifs += [r.upper(), O.reverse_complement(r.upper())]
+            assert np.array_equal(O.c_restriction(g, L, motifs), O.py_restriction(seqs, enz)), (L, enz)
