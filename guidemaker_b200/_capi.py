@@ -33,6 +33,7 @@ _SIGS = {
                        ctypes.POINTER(_vp), _c_i64p, _c_i64p],
     "gm_scan_fetch": [_vp, _vp, _vp, _vp],
     "gm_scan_free": [_vp],
+    "gm_gather_windows": [_vp, ctypes.c_int64, _vp, _vp, ctypes.c_int64, ctypes.c_int, _vp],
     "gm_seed_dedup": [_vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp],
     "gm_first_occurrence": [_vp, ctypes.c_int64, _vp],
     "gm_restriction_scan": [_vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp],
@@ -132,6 +133,19 @@ def pam_scan(seq: bytes | np.ndarray, pam: str, five_prime: bool, L: int):
     finally:
         lib.gm_scan_free(h)
     return g, s, p, nf.value, nr.value
+
+
+def gather_windows(seq: np.ndarray, win_start: np.ndarray, revcomp: np.ndarray, width: int) -> np.ndarray:
+    """(n_rows, width) uint8: window i of the ASCII buffer, reverse-complemented where flagged; windows outside the
+    buffer come back as '?' (the caller patches the few rows near record ends)."""
+    init()
+    seq = np.ascontiguousarray(seq, np.uint8)
+    win_start = np.ascontiguousarray(win_start, np.int64)
+    revcomp = np.ascontiguousarray(revcomp, np.uint8)
+    out = np.empty((len(win_start), int(width)), np.uint8)
+    _check(load_library().gm_gather_windows(_p(seq) if len(seq) else None, len(seq), _p(win_start), _p(revcomp), len(win_start),
+                                            int(width), _p(out)), "gm_gather_windows")
+    return out
 
 
 # ---- K2 ---------------------------------------------------------------------------------------------

@@ -138,7 +138,7 @@ class PamTarget:
         target_mat = decode_matrix(guides, L)
         df = pd.DataFrame({
             "target": _str_series(target_mat),
-            "exact_pam": pd.Categorical(_str_series(decode_matrix(pamcode.astype(np.uint64), P))),
+            "exact_pam": self._pam_categorical(pamcode, P),
             "start": start.astype(np.uint32),
             "stop": (start + L).astype(np.uint32),
             "strand": strand,
@@ -160,6 +160,17 @@ class PamTarget:
         return df
 
     @staticmethod
+    def _pam_categorical(pamcode: np.ndarray, P: int) -> pd.Categorical:
+        """exact_pam as pd.Categorical(strings) would build it -- categories = the distinct PAM strings in sorted
+        order -- from the packed codes by table look-up (no factorisation of n strings)."""
+        present = np.flatnonzero(np.bincount(pamcode, minlength=1 << 16))
+        cats = [b.decode() for b in decode_matrix(present.astype(np.uint64), P).view("S%d" % P).reshape(-1)] if P else [""] * len(present)
+        order = np.argsort(np.array(cats, dtype=object), kind="stable")
+        lut = np.zeros(1 << 16, dtype=np.int8 if len(present) < 128 else np.int32)
+        lut[present[order]] = np.arange(len(present))
+        return pd.Categorical.from_codes(lut[pamcode], categories=pd.Index([cats[i] for i in order], dtype="str"))
+
+    @staticmethod
     def _target_seq30(buf, seqs, rec, rec_start, lens, start, strand, five, P, L) -> pd.Series:
         """The 30-nt context column (core.py:156,184,210-211,237): a Python slice of the record
         around the match, reverse-complemented for reverse hits, NOT validated."""
@@ -173,22 +184,31 @@ class PamTarget:
         use_ms = strand == five                       # 5p fwd / 3p rev slice [ms-3, ms+27); others [me-27, me+3)
         a = np.where(use_ms, ms - 3, me - 27)
         interior = (a >= 0) & (a + 30 <= lens[rec])
-        out = np.empty((n, 30), dtype=np.uint8)
-        if len(buf) >= 30 and interior.any():
-            win = np.lib.stride_tricks.sliding_window_view(buf, 30)
-            out[interior] = win[(a + rec_start[rec])[interior]]
-        rev = interior & ~strand
-        if rev.any():
-            out[rev] = _COMP_LUT[out[rev][:, ::-1]]
+        # the gather (and the reverse complement of reverse-strand rows) runs on the GPU; rows whose window leaves
+        # their record are redirected outside the buffer and come back as '?'
+        out = _capi.gather_windows(buf, np.where(interior, a + rec_start[rec], -1), ~strand, 30)
         if interior.all():
             return _str_series(out)
-        out[~interior] = ord("?")
-        col = _str_series(out).astype(object)
-        for i in np.flatnonzero(~interior):           # near record ends: literal Python slicing, as the reference
+        # near record ends: literal Python slicing, as the reference -- the piece may be shorter than 30 or empty.
+        # The few exceptional rows are written left-aligned into the matrix and the column is assembled as ONE Arrow
+        # string array with per-row lengths (no detour through Python objects for the other rows).
+        import pyarrow as pa
+        width = np.full(n, 30, dtype=np.int64)
+        flat = out.reshape(-1)
+        parts, prev = [], 0
+        for i in np.flatnonzero(~interior):
             s = seqs[rec[i]]
             piece = s[int(a[i]): int(a[i]) + 30]
-            col.iat[i] = piece if strand[i] else _reverse_complement(piece)
-        return col.astype("str")
+            piece = (piece if strand[i] else _reverse_complement(piece)).encode("latin-1", "replace")
+            width[i] = len(piece)
+            parts.append(flat[prev * 30: i * 30])     # the untouched rows before this one, as a view
+            parts.append(np.frombuffer(piece, np.uint8))
+            prev = i + 1
+        parts.append(flat[prev * 30:])
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(width, out=offsets[1:])
+        arr = pa.LargeStringArray.from_buffers(n, pa.py_buffer(offsets), pa.py_buffer(np.concatenate(parts)))
+        return pd.Series(pd.array(arr, dtype="str"))
 
 
 class TargetProcessor:

@@ -353,6 +353,65 @@ extern "C" int gm_scan_create(const uint8_t *seq_ascii, int64_t n, const char *p
     return GM_OK;
 }
 
+// ---- sequence context windows (the target_seq30 column) ---------------------------------------------------------
+// find_targets also reports a 30-nt slice of the record around every match (core.py:156,184,210-211,237), reverse-
+// complemented for reverse-strand hits and NOT validated (it may contain N or lower case).  Row i copies `width` bytes
+// starting at win_start[i]; rows flagged in `revcomp` are reversed and complemented with Bio.Seq's IUPAC table
+// (other bytes unchanged).  A window that does not lie inside [0, n) is filled with '?' -- the host applies the
+// reference's literal Python slice semantics to those few rows near record ends.
+__constant__ uint8_t c_comp[256];
+
+__global__ void __launch_bounds__(256) gather_windows_kernel(const uint8_t *__restrict__ seq, int64_t n, const int64_t *__restrict__ win_start,
+                                                             const uint8_t *__restrict__ revcomp, int64_t n_rows, int width,
+                                                             uint8_t *__restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_rows * width) return;
+    const int64_t i = t / width;
+    const int j = (int)(t - i * width);
+    const int64_t a = win_start[i];
+    uint8_t c = (uint8_t)'?';
+    if (a >= 0 && a + width <= n) c = revcomp[i] ? c_comp[seq[a + width - 1 - j]] : seq[a + j];
+    out[t] = c;
+}
+
+extern "C" int gm_gather_windows(const uint8_t *seq_ascii, int64_t n, const int64_t *win_start, const uint8_t *revcomp, int64_t n_rows,
+                                 int width, uint8_t *out) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    GM_ARG(n >= 0 && n_rows >= 0 && width >= 1 && width <= 1024, "gm_gather_windows: bad size");
+    if (n_rows == 0) return GM_OK;
+    GM_ARG(win_start && revcomp && out && (n == 0 || seq_ascii), "gm_gather_windows: NULL buffer");
+    static bool table_set = false;
+    if (!table_set) {
+        uint8_t comp[256];
+        for (int c = 0; c < 256; c++) comp[c] = (uint8_t)c;
+        const char *from = "ACGTMRWSYKVHDBXNacgtmrwsykvhdbxn", *to = "TGCAKYWSRMBDHVXNtgcakywsrmbdhvxn";   // Bio.Seq complement
+        for (int k = 0; from[k]; k++) comp[(uint8_t)from[k]] = (uint8_t)to[k];
+        GM_CUDA(cudaMemcpyToSymbol(c_comp, comp, 256));
+        table_set = true;
+    }
+    uint8_t *d_seq = nullptr, *d_rc = nullptr, *d_out = nullptr;
+    int64_t *d_ws = nullptr;
+    cudaError_t e = dev_alloc((void **)&d_seq, (size_t)n + 16, 0);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_ws, (size_t)n_rows * 8, 0);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_rc, (size_t)n_rows, 0);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_out, (size_t)n_rows * width, 0);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(d_seq, seq_ascii, (size_t)n, cudaMemcpyHostToDevice, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_ws, win_start, (size_t)n_rows * 8, cudaMemcpyHostToDevice, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rc, revcomp, (size_t)n_rows, cudaMemcpyHostToDevice, 0);
+    if (e == cudaSuccess) {
+        const int64_t total = n_rows * width;
+        gather_windows_kernel<<<(unsigned)((total + 255) / 256), 256>>>(d_seq, n, d_ws, d_rc, n_rows, width, d_out);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n_rows * width, cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    dev_free(d_seq, 0); dev_free(d_ws, 0); dev_free(d_rc, 0); dev_free(d_out, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "gm_gather_windows", __FILE__, __LINE__);
+    return GM_OK;
+}
+
 extern "C" int gm_scan_fetch(void *scan, uint64_t *guide2bit, uint32_t *start, uint16_t *pamcode) {
     Scan *s = (Scan *)scan;
     GM_ARG(s, "gm_scan_fetch: NULL handle");

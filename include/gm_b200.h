@@ -8,6 +8,7 @@
  *
  *   gm_scan_*            regex.finditer(pam_regex, seq, overlapped=True) + slicing/revcomp/
  *                        check_target                                   core.py:142-246 (call sites :154,:182,:207,:234)
+ *   gm_gather_windows    the seq[...] slices (+ reverse_complement) behind target_seq30  core.py:156,184,210-211,237
  *   gm_seed_dedup        Series.duplicated() over the seed strings      core.py:402-416
  *   gm_first_occurrence  list(set(targets))  (made deterministic: first-occurrence order) core.py:446
  *   gm_restriction_scan  targets.str.contains('|'.join(expanded sites))  core.py:354-377 (call site :375)
@@ -73,6 +74,11 @@ int gm_scan_create(const uint8_t *seq_ascii, int64_t n, const char *pam, int pam
                    int five_prime, int L, void **scan, int64_t *n_fwd, int64_t *n_rev);
 int gm_scan_fetch(void *scan, uint64_t *guide2bit, uint32_t *start, uint16_t *pamcode);
 int gm_scan_free(void *scan);
+/* The 30-nt context column of find_targets (core.py:156,184,210-211,237): out[i*width + j] = byte j of the window
+ * starting at win_start[i] in seq_ascii; rows with revcomp[i] != 0 are reversed and complemented (Bio.Seq IUPAC
+ * table, other bytes unchanged).  Nothing is validated.  Windows not inside [0, n) are filled with '?'. */
+int gm_gather_windows(const uint8_t *seq_ascii, int64_t n, const int64_t *win_start, const uint8_t *revcomp,
+                      int64_t n_rows, int width, uint8_t *out);
 
 /* ---- K2: keep-first duplicate flags -----------------------------------------------------------
  * is_dup[i] = 1 iff an earlier row has the same seed (first lsr bases if five_prime, last lsr

@@ -167,6 +167,25 @@ def c_min_dist(targets, queries, L: int, metric: int, threads: int = 0):
     return dist
 
 
+def np_gather_windows(seq, win_start, revcomp, width: int) -> np.ndarray:
+    """target_seq30 windows (core.py:156,184,210-211,237) as plain numpy: slice, reverse-complement with Bio.Seq's
+    IUPAC table where flagged, '?' for windows outside the buffer."""
+    seq = np.ascontiguousarray(seq, np.uint8)
+    win_start = np.asarray(win_start, np.int64)
+    revcomp = np.asarray(revcomp).astype(bool)
+    lut = np.arange(256, dtype=np.uint8)
+    lut[np.frombuffer(b"ACGTMRWSYKVHDBXNacgtmrwsykvhdbxn", np.uint8)] = np.frombuffer(b"TGCAKYWSRMBDHVXNtgcakywsrmbdhvxn", np.uint8)
+    out = np.full((len(win_start), width), ord("?"), np.uint8)
+    ok = (win_start >= 0) & (win_start + width <= len(seq))
+    if ok.any():
+        idx = win_start[ok][:, None] + np.arange(width)[None, :]
+        rows = seq[idx]
+        rc = revcomp[ok]
+        rows[rc] = lut[rows[rc][:, ::-1]]
+        out[ok] = rows
+    return out
+
+
 def c_restriction(guides, L: int, motifs) -> np.ndarray:
     """bool[n]: guide contains one of the IUPAC motifs (the caller passes sites AND reverse complements)."""
     guides = np.ascontiguousarray(guides, np.uint64)

@@ -106,6 +106,7 @@ def oracle_engine(monkeypatch):
     monkeypatch.setattr(_capi, "pam_scan", pam_scan)
     monkeypatch.setattr(_capi, "seed_dedup", lambda g, L, lsr, five: O.c_seed_dedup(g, L, lsr, five))
     monkeypatch.setattr(_capi, "first_occurrence", lambda g: O.c_first_occurrence(g))
+    monkeypatch.setattr(_capi, "gather_windows", lambda seq, ws, rc, w: O.np_gather_windows(seq, ws, rc, w))
     monkeypatch.setattr(_capi, "restriction_scan", lambda g, L, motifs: O.c_restriction(g, L, motifs))
     monkeypatch.setattr(_capi, "Index", _OracleIndex)
     monkeypatch.setattr(_capi, "init", lambda device=None: None)

@@ -98,6 +98,21 @@ def test_scan_hits_at_record_ends(capi):
                 assert np.array_equal(a, b)
 
 
+def test_gather_windows_vs_numpy(capi):
+    """the target_seq30 gather (gm_gather_windows): forward and reverse-complemented windows, IUPAC letters, lower
+    case and N kept as Bio.Seq would, windows outside the buffer -> '?'"""
+    rng = np.random.default_rng(3)
+    seq = rng.choice(np.frombuffer(b"ACGTNRYKMSWBDHVXacgtnry-*", np.uint8), size=50021)
+    ws = rng.integers(-40, len(seq) + 10, size=30011)
+    ws[:6] = [0, len(seq) - 30, len(seq) - 29, -1, 1, len(seq)]
+    rc = rng.random(len(ws)) < 0.5
+    for width in (30, 1, 7):
+        got = capi.gather_windows(seq, ws, rc, width)
+        assert np.array_equal(got, O.np_gather_windows(seq, ws, rc, width)), width
+    assert capi.gather_windows(seq, ws[:0], rc[:0], 30).shape == (0, 30)
+    assert (capi.gather_windows(seq[:0], ws[:5], rc[:5], 30) == ord("?")).all()
+
+
 def test_scan_rejects_bad_pam(capi):
     with pytest.raises(ValueError):
         capi.pam_scan(b"ACGT" * 10, "NGZ", False, 20)
