@@ -14,26 +14,30 @@
 // bit-identical to K3a.
 //
 // What bounds this kernel is not arithmetic but the latency of the hand-offs between the roles (measured on B200 with
-// tools/tc_ablate.py: an mbarrier try_wait costs ~90 cycles even when it succeeds at once, the proxy fence after the
-// producers' stores ~150, a tcgen05.ld round trip ~150), so every role is spread over enough warps that its per-tile
+// tools/probes/tc_latency.cu: 3 MMAs + tcgen05.commit -> wake of a waiting warp 363 cycles, 219 of them the MMAs;
+// mbarrier.arrive -> try_wait wake in another warp 177; tcgen05.ld x32 + wait 124; try_wait on a completed phase 37;
+// the proxy fence after the producers' stores ~150), so every role is spread over enough warps that its per-tile
 // chain may take two tile periods, and nothing with a data-dependent duration sits on the MMA <-> epilogue cycle:
 //
 //   warps  0-15  epilogue: warp w reads TMEM lanes 32(w%4)..+31 (rows) of set (w>>3), accumulator buffer (w>>2)&1 --
 //                i.e. the even and the odd target tiles of a set have their own four warps.  A warp waits for its
 //                buffer, pulls 128 columns into registers, RELEASES the buffer at once (the next MMA can start) and only
-//                then ORs/ballots; flagged chunks go into a small shared-memory queue as (first target, row mask).
+//                then ORs/ballots; flagged chunks go into a small shared-memory queue as (first target, row mask) --
+//                one 8-byte store with a generation tag, no fence.
 //   warps 16-23  producers, two groups of four taking alternate tiles: planes -> one-hot B tile (one target per
 //                thread), canonical no-swizzle K-major layout, then proxy fence + arrive.
 //   warps 24-27  MMA issuers, one per (set, accumulator buffer) (elect.sync lane, operands in uniform registers): two
 //                try_waits, three MMAs and two tcgen05.commit (~95 cycles each) per tile are ~400 cycles of chain, more
 //                than the 384 cycles the tensor pipe needs for a tile, so an issuer only takes every other tile.  Warp 24
-//                owns the TMEM allocation; the commits publish accumulator buffers and release shared-memory stages.
+//                owns the TMEM allocation; the commits publish accumulator buffers and release shared-memory stages.  The
+//                two issuers of a set pass an issue token, so the set's tiles enter the tensor pipe in ascending order.
 //   warps 28-31  candidate warps: warp c serves the queues of TMEM quadrant c (both sets, both buffers) and is the
 //                exclusive owner of the lists and bounds of those 128 queries.  Per event lane j loads target j of the
 //                chunk (L2), all 32 exact distances of a flagged row's two queries are evaluated at once (2 LOP3 + POPC),
 //                hits are inserted by full (distance, index) key into lists kept in shared memory (so the order in
 //                which events of different tiles are served does not matter), and a tightened bound is written back
-//                into the bias byte of A (`fence.proxy.async`), where later MMAs pick it up.
+//                into the bias byte of A, where later MMAs pick it up.  Idle candidate warps poll every 2 us: every
+//                poll costs shared-memory cycles.
 //
 // Bit order.  The one-hot rows need byte m of word (chunk j, base b) = [base at position 4j+m is b].  The index keeps
 // a second copy of the planes with position p stored at bit (p>>2) + 8(p&3): then that word is (mask_b >> j) &
@@ -58,7 +62,7 @@ static constexpr int TC_QT = 256 * TC_SETS;                        // queries pe
 static constexpr int TC_EPI_WARPS = 8 * TC_SETS;                   // (set, buffer, quadrant)
 static constexpr int TC_PROD_WARP0 = TC_EPI_WARPS;
 static constexpr int TC_PROD_WARPS = 8;                            // two groups of four, alternate tiles
-static constexpr int TC_MMA_WARP = TC_PROD_WARP0 + TC_PROD_WARPS;  // first of TC_SETS issuer warps
+static constexpr int TC_MMA_WARP = TC_PROD_WARP0 + TC_PROD_WARPS;  // first of the issuer warps
 static constexpr int TC_MMA_WARPS = 2 * TC_SETS;                   // (set, buffer): each issues every other tile of its set
 static constexpr int TC_CAND_WARP0 = TC_MMA_WARP + TC_MMA_WARPS;
 static constexpr int TC_CAND_WARPS = 4;                            // one per TMEM lane quadrant
@@ -113,17 +117,6 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr, uint32_t lbo_byt
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
 }
-
-#define TC_LD_X32(r, taddr)                                                                                       \
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15," \
-                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                       \
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), \
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),       \
-                   "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),     \
-                   "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),     \
-                   "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                          \
-                 : "r"(taddr)                                                                                     \
-                 : "memory")
 
 // packed read: 32 registers cover 64 columns (two 16-bit values per register; the accumulators are <= 4030)
 #define TC_LD_X32_PACK(r, taddr)                                                                                  \
