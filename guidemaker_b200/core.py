@@ -85,6 +85,29 @@ def _series_matrix(s: pd.Series) -> np.ndarray:
     return as_byte_matrix(s)
 
 
+class _PackedStash:
+    """Packed guides riding along in ``DataFrame.attrs``.  pandas deep-copies ``attrs`` into every Series/frame derived
+    from the frame (``__finalize__``); the stash is immutable, so copies share it instead of duplicating 8 bytes per
+    row on every column access."""
+    __slots__ = ("crc", "shape", "guides")
+
+    def __init__(self, crc, shape, guides):
+        self.crc, self.shape, self.guides = crc, tuple(shape), guides
+        self.guides.setflags(write=False)
+
+    def __deepcopy__(self, memo):
+        return self
+
+    def __copy__(self):
+        return self
+
+    def __eq__(self, other):                           # pandas compares attrs when combining objects
+        return self is other
+
+    def __hash__(self):
+        return id(self)
+
+
 class PamTarget:
     """A Protospacer Adjacent Motif (PAM) and its targets (core.py:39-292)."""
 
@@ -156,7 +179,7 @@ class PamTarget:
         df["dtype"] = pd.Categorical.from_codes(np.zeros(n, dtype=np.int8), categories=[self.dtype])
         # The packed guides ride along so that TargetProcessor need not re-encode n strings; they are used only if
         # the CRC of the `target` column's bytes still matches (any edit, filter or reorder of the frame voids them).
-        df.attrs["_gm_packed"] = {"crc": zlib.crc32(target_mat), "shape": target_mat.shape, "guides": guides}
+        df.attrs["_gm_packed"] = _PackedStash(zlib.crc32(target_mat), target_mat.shape, guides)
         return df
 
     @staticmethod
@@ -252,9 +275,9 @@ class TargetProcessor:
         if cache is None or cache[0] != key:
             mat = self._guide_matrix()
             stash = self.targets.attrs.get("_gm_packed") if isinstance(self.targets.attrs, dict) else None
-            if (stash is not None and tuple(stash.get("shape", ())) == mat.shape and len(stash["guides"]) == len(mat)
-                    and stash.get("crc") == zlib.crc32(np.ascontiguousarray(mat))):
-                guides = stash["guides"]                       # produced by find_targets for exactly these strings
+            if (isinstance(stash, _PackedStash) and tuple(stash.shape) == mat.shape and len(stash.guides) == len(mat)
+                    and stash.crc == zlib.crc32(np.ascontiguousarray(mat))):
+                guides = stash.guides                          # produced by find_targets for exactly these strings
             else:
                 guides = encode_matrix(mat)
             cache = (key, guides, mat.shape[1], col.array)      # keep the array alive: ids stay unique
@@ -341,12 +364,12 @@ class TargetProcessor:
         idx, dist = sharded_knn(index, q, int(self.knum))
         if dist.shape[1] < 2 or (idx[:, 1] < 0).any():
             raise IndexError("list index out of range")    # editdist[1] with fewer than 2 hits (core.py:512,518)
-        keep = dist[:, 1] >= int(self.editdist)
+        rows = np.flatnonzero(dist[:, 1] >= int(self.editdist))           # kept query rows (core.py:518)
         group = None
         r2u = getattr(self, "_row2uniq", None)
         if r2u is not None and r2u[0] == self._packed_cache[0] and len(r2u[1]) == len(guides) and index.uniq is self.nmslib_index.uniq:
-            group = r2u[1][qmask][keep]
-        self.neighbors = NeighborMap(q[keep], idx[keep], dist[keep], index.uniq, L, group=group)
+            group = r2u[1][np.flatnonzero(qmask)[rows]]
+        self.neighbors = NeighborMap(q, idx, dist, index.uniq, L, group=group, rows=rows)
 
     def export_bed(self) -> object:
         """Rows with a first-seen seed as a BED-like frame sorted by (chrom, start) (core.py:525-543)."""

@@ -73,28 +73,34 @@ class ExactIndex:
 class NeighborMap(Mapping):
     """``neighbors[seq] -> {"target": seq, "neighbors": {"seqs": [...], "dist": [...]}}``."""
 
-    def __init__(self, qcodes: np.ndarray, idx: np.ndarray, dist: np.ndarray, uniq: np.ndarray, L: int, group=None):
-        """qcodes/idx/dist: the kept query rows in row order.  A dict keyed by the guide string keeps the first row of
-        every distinct guide, in order of first appearance (later rows carry identical values).  `group[i]` = any
-        integer id < len(uniq) that is equal for equal guides (e.g. the row's index in the distinct-guide table): with
-        it the dedupe is a linear scatter; without it, one stable sort."""
-        n = len(qcodes)
+    def __init__(self, qcodes: np.ndarray, idx: np.ndarray, dist: np.ndarray, uniq: np.ndarray, L: int, group=None, rows=None):
+        """qcodes/idx/dist: query rows in row order; `rows` (ascending indices, default all) selects the kept ones.
+        A dict keyed by the guide string keeps the first row of every distinct guide, in order of first appearance
+        (later rows carry identical values).  `group[i]` (one per kept row) = any integer id < len(uniq) that is equal
+        for equal guides (e.g. the row's index in the distinct-guide table): with it the dedupe is a linear scatter;
+        without it, one stable sort.  The big arrays are gathered once, with the composed index."""
+        if rows is None:
+            rows = np.arange(len(qcodes), dtype=np.int64)
+        codes = qcodes[rows]
+        n = len(codes)
         if group is not None and n:
             slot = np.full(len(uniq) if len(uniq) else 1, -1, dtype=np.int64)
             rev = np.arange(n - 1, -1, -1, dtype=np.int64)
             slot[np.asarray(group)[rev]] = rev               # repeated index: the last assignment wins = smallest row
             kept = np.flatnonzero(slot[group] == np.arange(n))
         else:
-            order = np.argsort(qcodes, kind="stable")
-            srt = qcodes[order]
+            order = np.argsort(codes, kind="stable")
+            srt = codes[order]
             head = np.ones(n, dtype=bool)
             head[1:] = srt[1:] != srt[:-1]
             keep_mask = np.zeros(n, dtype=bool)
             keep_mask[order[head]] = True                    # stable sort: smallest row of each group
             kept = np.flatnonzero(keep_mask)
-        self.codes = np.ascontiguousarray(qcodes[kept])
-        self.idx = idx[kept]
-        self.dist = dist[kept]
+        final = rows[kept]
+        whole = len(final) == len(qcodes)                    # nothing dropped: no copy at all
+        self.codes = np.ascontiguousarray(qcodes if whole else codes[kept])
+        self.idx = idx if whole else idx[final]
+        self.dist = dist if whole else dist[final]
         self.uniq, self.L = uniq, int(L)
         self._sorted = self._pos = None                      # lookup index, built on first use
 
