@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256) mb_kernel(uint32_t *out, int iters) {
 extern "C" int gm_microbench(int what, double *ops_per_s) {
     int rc = ensure_init();
     if (rc) return rc;
-    GM_ARG(what >= 0 && what <= 8 && ops_per_s, "gm_microbench: what must be 0..8");
+    GM_ARG(what >= 0 && what <= 11 && ops_per_s, "gm_microbench: what must be 0..11");
     if (what >= 3) return microbench_mma_i8(what - 3, ops_per_s);
     uint32_t *d = nullptr;
     GM_CUDA(dev_alloc((void **)&d, 64, 0));

@@ -394,6 +394,7 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
             unsigned long long h[56];
             GM_CUDA(cudaStreamSynchronize(st));
             GM_CUDA(cudaMemcpy(h, d_dbg, sizeof h, cudaMemcpyDeviceToHost));
+            // (the counters are compiled in with -DGM_TC_STATS, see tools/tc_ablate.py; otherwise they read 0)
             fprintf(stderr, "[tc_dbg] candidate events %llu (%.2f per query), list inserts %llu (%.2f per query), grid %u x %d; "
                     "epilogue warps: %.1f %% of their time behind a full candidate queue (%llu stalls)\n", h[0],
                     (double)h[0] / (double)q, h[1], (double)h[1] / (double)q, (unsigned)(q_pad / tc_query_tile()), list_splits,

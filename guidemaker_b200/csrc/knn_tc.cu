@@ -26,11 +26,14 @@
 //                one 8-byte store with a generation tag, no fence.
 //   warps 16-23  producers, two groups of four taking alternate tiles: planes -> one-hot B tile (one target per
 //                thread), canonical no-swizzle K-major layout, then proxy fence + arrive.
-//   warps 24-27  MMA issuers, one per (set, accumulator buffer) (elect.sync lane, operands in uniform registers): two
-//                try_waits, three MMAs and two tcgen05.commit (~95 cycles each) per tile are ~400 cycles of chain, more
-//                than the 384 cycles the tensor pipe needs for a tile, so an issuer only takes every other tile.  Warp 24
-//                owns the TMEM allocation; the commits publish accumulator buffers and release shared-memory stages.  The
-//                two issuers of a set pass an issue token, so the set's tiles enter the tensor pipe in ascending order.
+//   warps 24-27  MMA issuers, one per (set, accumulator buffer) (elect.sync lane, operands in uniform registers), each
+//                taking every other tile of its set: wait for the B stage and for the buffer, three MMAs, ONE
+//                tcgen05.commit that publishes the buffer.  A commit stalls the issuing thread until its MMAs have
+//                completed (gm_microbench 9-11: three MMAs take 228 cycles of one issuing thread, 467 with one commit
+//                behind them, 604 with two), so the shared-memory stage is NOT released by a second commit but by a
+//                plain arrive two tiles later, when the issuer has seen the buffer of that tile read out; six stages keep
+//                the producers four tiles ahead all the same.  Warp 24 owns the TMEM allocation.  The two issuers of a
+//                set pass an issue token, so the set's tiles enter the tensor pipe in ascending order.
 //   warps 28-31  candidate warps: warp c serves the queues of TMEM quadrant c (both sets, both buffers) and is the
 //                exclusive owner of the lists and bounds of those 128 queries.  Per event lane j loads target j of the
 //                chunk (L2), all 32 exact distances of a flagged row's two queries are evaluated at once (2 LOP3 + POPC),
@@ -50,14 +53,15 @@ namespace gm {
 // Timing-only ablations (tools/tc_ablate.py; results are wrong by construction): 1 = epilogue skips the TMEM loads,
 // 2 = producers skip the one-hot expansion, 4 = issuers skip the MMAs (commits only), 8 = candidate path disabled,
 // 16 = producers skip the proxy fence, 32 = producers do not wait for the stage to be released,
-// 128 = candidate warps pop events but do not serve them, 256 = one MMA K step fewer per tile.
+// 128 = candidate warps pop events but do not serve them, 256 = one MMA K step fewer per tile,
+// 512 = flags are evaluated and voted on but nothing is queued.
 #ifndef GM_TC_ABL
 #define GM_TC_ABL 0
 #endif
 static constexpr int TC_M = 128;           // rows per A operand
 static constexpr int TC_N = 128;           // targets per tile
 static constexpr int TC_SETS = 2;          // A operands (query tiles) per CTA
-static constexpr int TC_STAGES = 4;        // B tiles in shared memory
+static constexpr int TC_STAGES = 6;        // B tiles in shared memory (even: a stage always serves the same producer group)
 static constexpr int TC_QT = 256 * TC_SETS;                        // queries per CTA
 static constexpr int TC_EPI_WARPS = 8 * TC_SETS;                   // (set, buffer, quadrant)
 static constexpr int TC_PROD_WARP0 = TC_EPI_WARPS;
@@ -151,10 +155,26 @@ __device__ __forceinline__ uint4 onehot_chunk(uint32_t eA, uint32_t eC, uint32_t
     return make_uint4((eA >> j) & 0x01010101u, (eC >> j) & 0x01010101u, (eG >> j) & 0x01010101u, (eT >> j) & 0x01010101u);
 }
 
-// a spin loop outlived ~10 s: fail the launch instead of hanging the GPU (1 = issue order, 2 = candidate queue)
+// a spin loop outlived ~10 s: fail the launch instead of hanging the GPU (1 = issue order, 2 = candidate queue, 3 = mbarrier)
 __device__ __noinline__ void tc_watchdog(int what) {
     printf("libgm_b200: K3b watchdog %d fired (block %d,%d thread %d)\n", what, blockIdx.x, blockIdx.y, threadIdx.x);
     __trap();
+}
+// mbarrier wait for the role loops: the first try is inline, the spin (with its watchdog: clock, counter, printf
+// arguments) lives in an outlined function so that it costs the callers no registers.
+__device__ __noinline__ void tc_wait_slow(uint64_t *bar, uint32_t parity) {
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity))
+        if ((++spins & 0xFFFu) == 0 && clock64() - t0 > 20000000000LL) tc_watchdog(3);
+}
+__device__ __forceinline__ void tc_wait(uint64_t *bar, uint32_t parity) {
+    if (!mbar_try_wait(bar, parity)) tc_wait_slow(bar, parity);
+}
+// OR of 16 registers as a depth-3 tree of 3-input LOP3s (a serial chain would be 8 deep)
+__device__ __forceinline__ uint32_t tc_or16(const uint32_t *r) {
+    const uint32_t a = r[0] | r[1] | r[2], b = r[3] | r[4] | r[5], c = r[6] | r[7] | r[8], d = r[9] | r[10] | r[11], e = r[12] | r[13] | r[14];
+    return (a | b | c) | (d | e | r[15]);
 }
 __device__ __forceinline__ uint32_t ld_vol(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
 __device__ __forceinline__ void st_vol(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
@@ -204,7 +224,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
     const int64_t qbase = ((int64_t)blockIdx.x + a.tile_offset) * TC_QT;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&b_full[s], 4); mbar_init(&b_empty[s], TC_SETS); }
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&b_full[s], 4); mbar_init(&b_empty[s], TC_SETS); }   // b_empty: one arrive per set
         for (int q = 0; q < TC_SETS; q++)
             for (int b = 0; b < 2; b++) { mbar_init(&acc_full[q][b], 1); mbar_init(&acc_empty[q][b], 4); }
         mbar_fence_init();
@@ -278,36 +298,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
         const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)set * (2 * TC_N) + (uint32_t)par * TC_N;
         uint2 *queue = sQueue + warp * TC_QN;
         uint32_t tail = 0;
+#ifdef GM_TC_STATS                                                  // -DGM_TC_STATS + GM_TC_DEBUG=1: queue stalls, tile-rate profile
         uint32_t stall_clk = 0, n_stalls = 0;                       // lane 0: time (units of 64 cycles) spent behind a full candidate queue
         const long long t_begin = clock64();
+#endif
         uint32_t r[32];
         for (int i = par; i < n_tiles; i += 2) {
-            mbar_wait(&acc_full[set][par], (uint32_t)((i >> 1) & 1));
+            tc_wait(&acc_full[set][par], (uint32_t)((i >> 1) & 1));
             tc_fence_after();
-            if (a.dbg && (i & 255) == 0 && (i >> 8) < 48 && blockIdx.x + a.tile_offset == 200 && warp == 0 && lane == 0)     // GM_TC_DEBUG: tile-rate profile of one CTA
+#ifdef GM_TC_STATS
+            if (a.dbg && (i & 255) == 0 && (i >> 8) < 48 && blockIdx.x + a.tile_offset == 200 && warp == 0 && lane == 0)     // tile-rate profile of one CTA
                 a.dbg[8 + (i >> 8)] = (unsigned long long)(clock64() - t_begin);
+#endif
             uint32_t f[4];
 #if GM_TC_ABL & 1
             f[0] = f[1] = f[2] = f[3] = 0u;
 #else
-#pragma unroll
-            for (int h = 0; h < 2; h++) {             // 64 columns per packed load: registers 0..15 = columns 0..31, 16..31 = 32..63
-                TC_LD_X32_PACK(r, taddr + h * 64);
-                tc_wait_ld();
-                uint32_t f0 = 0, f1 = 0;
-#pragma unroll
-                for (int x = 0; x < 16; x += 2) { f0 |= r[x] | r[x + 1]; f1 |= r[16 + x] | r[16 + x + 1]; }
-                f[2 * h] = f0;
-                f[2 * h + 1] = f1;
-            }
+            // 64 columns per packed load: registers 0..15 = columns 0..31, 16..31 = columns 32..63.  Everything between the
+            // buffer's commit and its release is on the MMA -> read-out -> MMA round trip, so the first load is reduced
+            // by a depth-3 OR tree (the registers are needed for the second load) and the second load's registers are only
+            // reduced AFTER the release.  (A serial OR chain of all 64 registers before the release cost 12 ms of 66.)
+            TC_LD_X32_PACK(r, taddr);
+            tc_wait_ld();
+            f[0] = tc_or16(r);
+            f[1] = tc_or16(r + 16);
+            TC_LD_X32_PACK(r, taddr + 64);
+            tc_wait_ld();
 #endif
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[set][par]);       // buffer released before any candidate work
+            if (lane == 0) mbar_arrive(&acc_empty[set][par]);       // buffer released before any further work
+#if !(GM_TC_ABL & 1)
+            f[2] = tc_or16(r);
+            f[3] = tc_or16(r + 16);
+#endif
             // One vote says whether anything in the tile is flagged (usually not); then one event per flagged chunk.
             // (One event per tile with the union of the rows was measured slower: the candidate warp's extra shared-memory
             // reads cost more than the pushes they save -- shared-memory cycles are what this kernel runs out of.)
-            if (__any_sync(0xFFFFFFFFu, ((f[0] | f[1] | f[2] | f[3]) & TC_FLAGS) != 0) && !(GM_TC_ABL & 8)) {
+#if GM_TC_ABL & 512                                                  // flags evaluated and voted on, nothing queued
+            if (__any_sync(0xFFFFFFFFu, ((f[0] | f[1] | f[2] | f[3]) & TC_FLAGS) != 0)) tail++;
+#endif
+            if (__any_sync(0xFFFFFFFFu, ((f[0] | f[1] | f[2] | f[3]) & TC_FLAGS) != 0) && !(GM_TC_ABL & (8 | 512))) {
                 const uint32_t t0 = (uint32_t)(tile0 + i) * TC_N;
 #pragma unroll
                 for (int h = 0; h < 4; h++) {
@@ -320,8 +351,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
                                 __nanosleep(256);
                                 if (clock64() - w0 > 20000000000LL) tc_watchdog(2);
                             }
+#ifdef GM_TC_STATS
                             stall_clk += (uint32_t)((clock64() - w0) >> 6);
                             n_stalls++;
+#endif
                         }
                         // One 8-byte store publishes the event: bit 31 of the first word is a generation tag that flips on
                         // every lap of the ring, so the consumer polls the slot itself and no fence (MEMBAR, ~200 cycles
@@ -335,12 +368,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
             }
         }
         __syncwarp();
+#if GM_TC_ABL & 512
+        if (tail == 0xFFFFFFFFu) a.lists[0] = tail;                 // keeps the vote alive
+#endif
         if (lane == 0) { __threadfence_block(); atomicAdd(&s_done, 1u); }
+#ifdef GM_TC_STATS
         if (a.dbg && lane == 0) {
             atomicAdd(&a.dbg[2], (unsigned long long)stall_clk << 6);
             atomicAdd(&a.dbg[3], (unsigned long long)n_stalls);
             atomicAdd(&a.dbg[4], (unsigned long long)(clock64() - t_begin));
         }
+#endif
     } else if (warp < TC_MMA_WARP) {
         // ================= producers: planes -> one-hot B tile (one target per thread, group g takes tiles g, g+2, ..) ===
         const int pw = warp - TC_PROD_WARP0, grp = pw >> 2, p = (pw & 3) * 32 + lane;
@@ -352,7 +390,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
             const uint2 tp = tnext;
             if (i + 2 < n_tiles) tnext = tsrc[(size_t)(i + 2) * TC_N];       // prefetch this thread's next target
             const uint32_t eA = ~(tp.x | tp.y) & lmask, eC = tp.x & ~tp.y, eG = tp.y & ~tp.x, eT = tp.x & tp.y;
-            if (round > 0 && !(GM_TC_ABL & 32)) mbar_wait(&b_empty[s], (round - 1) & 1u);
+            if (round > 0 && !(GM_TC_ABL & 32)) tc_wait(&b_empty[s], (round - 1) & 1u);
             uint8_t *dstp = sB + (size_t)s * b_bytes + (size_t)p * 16;
 #pragma unroll
             for (int j = 0; j < ((GM_TC_ABL & 2) ? 0 : kc); j++) {  // positions beyond L have all-zero masks
@@ -374,7 +412,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
         const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem, 0);
         const uint32_t sA_u = __shfl_sync(0xFFFFFFFFu, smem_u32(sA), 0), sB_u = __shfl_sync(0xFFFFFFFFu, smem_u32(sB), 0);
         const uint32_t bar_f = __shfl_sync(0xFFFFFFFFu, smem_u32(&acc_full[q][par]), 0);
-        const uint32_t bar_bempty_u = __shfl_sync(0xFFFFFFFFu, smem_u32(&b_empty[0]), 0);
         const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
         // descriptors differ only in the start-address field (low 14 bits, units of 16 bytes): build once, add offsets
         const uint64_t da = tc_desc(sA_u + (uint32_t)q * a_bytes, TC_M * 16, 128);
@@ -385,8 +422,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
         const uint32_t d = tmem_u + (uint32_t)q * (2 * TC_N) + (uint32_t)par * TC_N;
         for (int i = par; i < n_tiles; i += 2) {
             const int s = i % TC_STAGES;
-            mbar_wait(&b_full[s], (uint32_t)((i / TC_STAGES) & 1));
-            if (i >= 2) mbar_wait(&acc_empty[q][par], (uint32_t)(((i >> 1) - 1) & 1));
+            tc_wait(&b_full[s], (uint32_t)((i / TC_STAGES) & 1));
+            if (i >= 2) {
+                tc_wait(&acc_empty[q][par], (uint32_t)(((i >> 1) - 1) & 1));
+                // Tile i - 2 of this set has been multiplied AND read out, so the set is done with its B stage: release it
+                // here with a plain arrive.  (A second tcgen05.commit right after the MMAs would release it earlier, but a
+                // commit stalls the issuing thread until its MMAs have completed -- measured: 3 MMAs + 1 commit take 467
+                // cycles of a single issuing thread, + 2 commits 604, against 228 without -- and the issue path is what
+                // this kernel runs out of.  TC_STAGES = 6 keeps the producers four tiles ahead all the same.)
+                if (leader) mbar_arrive(&b_empty[(i - 2) % TC_STAGES]);
+            }
             // The two issuers of a set take turns: tiles enter the tensor pipe in ascending order, so the bias bytes an
             // MMA reads can only reflect list entries from EARLIER tiles (lower target indices) -- what makes "flag iff
             // strictly closer than the k-th best" exact under the (distance, index) order.
@@ -399,22 +444,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
             }
             tc_fence_after();
             const uint64_t db = db0 + (uint64_t)((uint32_t)s * b_stage);
-            const uint32_t bar_e = bar_bempty_u + (uint32_t)(s * 8);
             if (leader) {
 #pragma unroll
                 for (int ks = 0; ks < ((GM_TC_ABL & 4) ? 0 : (GM_TC_ABL & 256) ? n_ks - 1 : n_ks); ks++)
                     tc_mma_i8(d, da + (uint64_t)((uint32_t)ks * a_ks), db + (uint64_t)((uint32_t)ks * b_ks), idesc, ks > 0 ? 1u : 0u);
                 __threadfence_block();
                 st_vol(&s_issued[q], (uint32_t)i + 1u);             // the set's other issuer may go ahead
-                tc_commit_addr(bar_f);                              // accumulator buffer ready for its epilogue warps
-                tc_commit_addr(bar_e);                              // this issuer is done with the smem stage
+                tc_commit_addr(bar_f);                              // accumulator buffer ready for its epilogue warps (which
+                                                                    // also release the smem stage)
             }
             __syncwarp();
         }
     } else {
         // ================= candidate warps: warp c owns the queries of TMEM quadrant c of both sets ====================
         const int c = warp - TC_CAND_WARP0;
+#ifdef GM_TC_STATS
         unsigned long long n_events = 0, n_inserts = 0;
+#define TC_STAT(x) x
+#else
+#define TC_STAT(x)
+#endif
         // one event = (first target of a 32-target chunk, mask of flagged rows); `set` selects the A operand
         auto serve = [&](const uint2 ev, const uint2 tp, const int set) {
             uint32_t fl = ev.y;
@@ -446,7 +495,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
                             if (lane == 0) w = list_insert_smem(lst, a.k, ki);
                             w = __shfl_sync(0xFFFFFFFFu, w, 0);
                             bound = min(bound, w);
-                            n_inserts++;
+                            TC_STAT(n_inserts++);
                         }
                     }
                     if (bound != bound0 && lane == 0) {
@@ -498,9 +547,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
             }
 #pragma unroll
             for (int x = 0; x < 4; x++)
-                if (have[x]) { if (!(GM_TC_ABL & 128)) serve(ev[x], tp[x], x >> 1); n_events++; }
+                if (have[x]) { if (!(GM_TC_ABL & 128)) serve(ev[x], tp[x], x >> 1); TC_STAT(n_events++); }
         }
-        if (a.dbg && lane == 0) { atomicAdd(&a.dbg[0], n_events); atomicAdd(&a.dbg[1], n_inserts); }
+        TC_STAT(if (a.dbg && lane == 0) { atomicAdd(&a.dbg[0], n_events); atomicAdd(&a.dbg[1], n_inserts); })
     }
 
     tc_fence_before();
@@ -527,14 +576,18 @@ __device__ __forceinline__ void tc_mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-template <int N, bool A_TMEM, bool CYCLE = false>
+template <int N, bool A_TMEM, bool CYCLE = false, int COMMITS = 0>
 __global__ void __launch_bounds__(128, 1) mb_mma_i8_kernel(int n_mma, unsigned long long *cycles) {
     extern __shared__ __align__(1024) uint8_t smem[];          // operands: contents irrelevant for throughput
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t bar, side[8];             // side: targets of the COMMITS extra commits per three MMAs
     __shared__ uint32_t s_base;
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < (CYCLE ? 64 * 1024 : (128 + 256) * 32) / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x01010101u;
-    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        for (int b = 0; b < 8; b++) mbar_init(&side[b], 1);
+        mbar_fence_init();
+    }
     fence_async_smem();
     if (warp == 0) tc_alloc(&s_base, 512);
     tc_fence_before();
@@ -554,7 +607,11 @@ __global__ void __launch_bounds__(128, 1) mb_mma_i8_kernel(int n_mma, unsigned l
             const uint64_t oa = CYCLE ? (uint64_t)(ia * (4096 >> 4)) : 0, ob = CYCLE ? (uint64_t)((3 + ib) * (4096 >> 4)) : 0;
             if (A_TMEM) tc_mma_i8_ts(d, s_base + 256 + (CYCLE ? (uint32_t)ia * 8u : 0u), db + ob - (CYCLE ? 128 * 32 / 16 : 0), idesc, i > 1 ? 1u : 0u);
             else tc_mma_i8(d, da + oa, db + ob - (CYCLE ? 128 * 32 / 16 : 0), idesc, i > 1 ? 1u : 0u);
-            if (++ia == 3) ia = 0;
+            if (++ia == 3) {
+                ia = 0;
+                // the kNN kernel's pattern: COMMITS tcgen05.commit after every group of three MMAs (nobody waits on them here)
+                for (int c = 0; c < COMMITS; c++) tc_commit(&side[(i + c) & 7]);
+            }
             if (++ib == 12) ib = 0;
         }
         tc_commit(&bar);
@@ -568,11 +625,11 @@ __global__ void __launch_bounds__(128, 1) mb_mma_i8_kernel(int n_mma, unsigned l
 
 // int8 tensor ops/s (2 per MAC) of the whole GPU, timed with CUDA events.  variant 0: N = 256 SS (the roofline
 // denominator), 1: N = 128 SS, 2: N = 128 TS, 3: N = 256 TS (A operand in tensor memory).
-template <int N, bool A_TMEM, bool CYCLE = false>
+template <int N, bool A_TMEM, bool CYCLE = false, int COMMITS = 0>
 static int microbench_mma_i8_t(double *ops_per_s) {
     static bool attr_set = false;
     if (!attr_set) {
-        GM_CUDA(cudaFuncSetAttribute(mb_mma_i8_kernel<N, A_TMEM, CYCLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+        GM_CUDA(cudaFuncSetAttribute(mb_mma_i8_kernel<N, A_TMEM, CYCLE, COMMITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
         attr_set = true;
     }
     unsigned long long *d = nullptr;
@@ -584,7 +641,7 @@ static int microbench_mma_i8_t(double *ops_per_s) {
     float best = 1e30f;
     for (int rep = 0; rep < 3; rep++) {
         GM_CUDA(cudaEventRecord(e0));
-        mb_mma_i8_kernel<N, A_TMEM, CYCLE><<<grid, 128, 116 * 1024>>>(n_mma, d);      // > half the SM's shared memory: one CTA per SM
+        mb_mma_i8_kernel<N, A_TMEM, CYCLE, COMMITS><<<grid, 128, 116 * 1024>>>(n_mma, d);      // > half the SM's shared memory: one CTA per SM
         count_launch();
         GM_CUDA(cudaEventRecord(e1));
         GM_CUDA(cudaEventSynchronize(e1));
@@ -606,6 +663,9 @@ int microbench_mma_i8(int variant, double *ops_per_s) {
     case 3: return microbench_mma_i8_t<256, true>(ops_per_s);
     case 4: return microbench_mma_i8_t<128, false, true>(ops_per_s);
     case 5: return microbench_mma_i8_t<128, true, true>(ops_per_s);
+    case 6: return microbench_mma_i8_t<128, false, true, 1>(ops_per_s);
+    case 7: return microbench_mma_i8_t<128, false, true, 2>(ops_per_s);
+    case 8: return microbench_mma_i8_t<64, false, true, 2>(ops_per_s);
     default: return microbench_mma_i8_t<256, false>(ops_per_s);
     }
 }

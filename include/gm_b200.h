@@ -141,7 +141,8 @@ int gm_knn_engine(int engine);
  * what = 0: POPC, 1: LOP3, 2: IMAD -> register-resident lane-operations per second;
  * what = 3: back-to-back tcgen05.mma kind::i8 (128x256x32, both operands in shared memory) -> int8 tensor
  *           operations per second (2 per MAC); 4: 128x128x32; 5 / 6: 128x128x32 / 128x256x32 with A in tensor memory;
- *           7 / 8: 128x128x32 SS / TS with consecutive MMAs reading different operand tiles (as the kNN kernel does). */
+ *           7 / 8: 128x128x32 SS / TS with consecutive MMAs reading different operand tiles (as the kNN kernel does);
+ *           9 / 10: as 7 with one / two tcgen05.commit after every three MMAs; 11: as 10 with 128x64x32 MMAs. */
 int gm_microbench(int what, double *ops_per_s);
 
 #ifdef __cplusplus

@@ -68,7 +68,7 @@ def run(names):
         names = sorted(f[6:-3] for f in os.listdir(VAR) if f.startswith("libgm_") and f.endswith(".so"))
     out = {}
     for name in names:
-        lib, _, opt = name.partition("+")                    # NAME+dbg: same library with GM_TC_DEBUG=1 (event counters)
+        lib, _, opt = name.partition("+")                    # NAME+dbg: same library with GM_TC_DEBUG=1 (event counters; build it with -DGM_TC_STATS)
         env = dict(os.environ, GM_B200_LIB=os.path.join(VAR, f"libgm_{lib}.so"))
         if opt == "dbg":
             env["GM_TC_DEBUG"] = "1"
