@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = a.L;
-    const int nd = (L + 3) >> 2;                      // data chunks; chunk nd carries the bias bytes
+    const int nd = (L + 3) >> 2;                      // data chunks 0 .. nd-1 (nd < kc)
+    constexpr int kb = kc - 1;                        // the LAST chunk carries the bias bytes: a compile-time position
     const uint32_t lmask = tc_permute_bits((1u << L) - 1u);
     const uint32_t a_bytes = (uint32_t)TC_M * 16u * (uint32_t)kc;
     const uint32_t b_bytes = (uint32_t)TC_N * 16u * (uint32_t)kc;
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
                 const uint4 w0 = onehot_chunk(e[0][0], e[0][1], e[0][2], e[0][3], j);
                 const uint4 w1 = onehot_chunk(e[1][0], e[1][1], e[1][2], e[1][3], j);
                 w = make_uint4(w0.x + 64u * w1.x, w0.y + 64u * w1.y, w0.z + 64u * w1.z, w0.w + 64u * w1.w);
-            } else if (j == nd) {
+            } else if (j == kb) {
                 w.x = (uint32_t)(31 - L + (int)tau[0]) | ((uint32_t)(31 - L + (int)tau[1]) << 8);
             }
             *reinterpret_cast<uint4 *>(myA + (size_t)j * (TC_M * 16) + (size_t)row * 16) = w;
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
 #pragma unroll
             for (int j = 0; j < ((GM_TC_ABL & 2) ? 0 : kc); j++) {  // positions beyond L have all-zero masks
                 uint4 w = onehot_chunk(eA, eC, eG, eT, j);
-                if (j == nd) w.x = 1u | (64u << 8);                 // multiplies the bias bytes of A: 1 * b1 + 64 * b2
+                if (j == kb) w.x = 1u | (64u << 8);                 // multiplies the bias bytes of A: 1 * b1 + 64 * b2
                 *reinterpret_cast<uint4 *>(dstp + j * (TC_N * 16)) = w;
             }
             if (!(GM_TC_ABL & 16)) fence_async_smem();              // generic-proxy writes -> visible to the tensor core
@@ -503,7 +504,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
                         // tighten the bias byte; later MMAs pick it up.  No proxy fence: the byte only has to reach the
                         // tensor core eventually (measured: the fence changes nothing)
                         if ((bound >> IDX_BITS) != (bound0 >> IDX_BITS))
-                            sA[(size_t)set * a_bytes + (size_t)nd * (TC_M * 16) + (size_t)row * 16 + e] =
+                            sA[(size_t)set * a_bytes + (size_t)kb * (TC_M * 16) + (size_t)row * 16 + e] =
                                 (uint8_t)(31 - L + (int)(bound >> IDX_BITS));
                     }
                     __syncwarp();
