@@ -1,0 +1,108 @@
+"""CPU model of the K3b filter protocol (guidemaker_b200/csrc/knn_tc.cu) -- checks the ARGUMENT, not the kernel.
+
+The tensor-core pass only produces flags "target t is strictly closer to query q than q's current bound"; the bound an
+MMA sees (the bias byte of A) may be stale, and the candidate warps serve the flagged (tile, query) events in any
+order, inserting by full (distance, index) key.  The kernel's claim: as long as the tiles of a query enter the tensor
+pipe in ASCENDING order, the final lists equal the exact top-k under (distance, index) whatever the staleness and the
+service order.  This model draws random staleness and service orders and compares with brute force; it also shows
+that the claim fails when tiles may overtake each other (the bug the issue token in the kernel prevents)."""
+import numpy as np
+import pytest
+
+KEY_EMPTY = np.iinfo(np.int64).max
+
+
+def brute_topk(dist_row, k):
+    order = np.lexsort((np.arange(len(dist_row)), dist_row))[:k]
+    return [(int(dist_row[i]), int(i)) for i in order]
+
+
+def run_protocol(dist, k, tile, rng, in_order=True, max_lag=6, warm=0):
+    """dist: (Q, N) exact distances.  Returns per-query sorted lists of (distance, index)."""
+    Q, N = dist.shape
+    n_tiles = (N + tile - 1) // tile
+    lists = [[] for _ in range(Q)]                     # sorted by (d, idx), at most k entries
+    bound = [(np.inf, np.inf)] * Q                     # insert iff key < bound (full key)
+    bias = np.full(Q, np.inf)                          # what the MMA compares with: flag iff d < bias (strict)
+    if warm:                                           # warm start: lists of the first `warm` targets are inherited
+        for q in range(Q):
+            lists[q] = brute_topk(dist[q, :warm], k)
+            if len(lists[q]) == k:
+                bound[q] = lists[q][-1]
+                bias[q] = lists[q][-1][0]
+    first = warm // tile
+    order = list(range(first, n_tiles))
+    if not in_order:                                   # tiles may overtake each other by a few positions
+        for i in range(len(order) - 1):
+            if rng.random() < 0.5:
+                order[i], order[i + 1] = order[i + 1], order[i]
+    pending = []                                       # queued events: (ready_time, tile, q)
+    pending_bias = []                                  # bound tightenings on their way to the bias byte: (time, q, d)
+    clock = 0
+    for t in order:
+        clock += 1
+        # bias updates that have "landed" by now
+        for item in [p for p in pending_bias if p[0] <= clock]:
+            bias[item[1]] = min(bias[item[1]], item[2])
+        pending_bias = [p for p in pending_bias if p[0] > clock]
+        lo, hi = t * tile, min((t + 1) * tile, N)
+        flagged = (dist[:, lo:hi] < bias[:, None]).any(axis=1)          # the accumulator filter, per query
+        for q in np.flatnonzero(flagged):
+            pending.append((clock + int(rng.integers(0, max_lag)), t, int(q)))
+        # candidate warps: serve a random subset of the ready events, in random order
+        ready = [e for e in pending if e[0] <= clock]
+        rng.shuffle(ready)
+        served = ready[: int(rng.integers(0, len(ready) + 1))] if clock < len(order) else ready
+        for e in served:
+            pending.remove(e)
+            _, tt, q = e
+            a, b = tt * tile, min((tt + 1) * tile, N)
+            for i in range(a, b):                      # exact re-check of every target of the chunk
+                key = (int(dist[q, i]), i)
+                if key < bound[q]:
+                    lists[q].append(key)
+                    lists[q].sort()
+                    del lists[q][k:]
+                    if len(lists[q]) == k:
+                        bound[q] = min(bound[q], lists[q][-1])
+                        pending_bias.append((clock + int(rng.integers(0, max_lag)), q, lists[q][-1][0]))
+    for _, tt, q in pending:                           # drain
+        a, b = tt * tile, min((tt + 1) * tile, N)
+        for i in range(a, b):
+            key = (int(dist[q, i]), i)
+            if key < bound[q]:
+                lists[q].append(key)
+                lists[q].sort()
+                del lists[q][k:]
+                if len(lists[q]) == k:
+                    bound[q] = min(bound[q], lists[q][-1])
+    return lists
+
+
+def small_case(rng, Q=24, N=700, L=6):
+    q = rng.integers(0, 4, size=(Q, L))
+    t = rng.integers(0, 4, size=(N, L))
+    return (q[:, None, :] != t[None, :, :]).sum(axis=2)               # many ties: distances in 0..6
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_filter_protocol_is_exact_for_any_staleness_and_service_order(seed):
+    rng = np.random.default_rng(seed)
+    dist = small_case(rng)
+    k = int(rng.choice([1, 2, 3, 5]))
+    warm = int(rng.choice([0, 64, 128]))
+    lists = run_protocol(dist, k, tile=32, rng=rng, in_order=True, warm=warm)
+    for q in range(dist.shape[0]):
+        assert lists[q] == brute_topk(dist[q], k), (seed, q)
+
+
+def test_out_of_order_tiles_can_lose_ties():
+    """Without the issue token a later tile's entry can tighten the bias before an earlier tile is multiplied; a target
+    of the earlier tile at exactly that distance is then not flagged although it wins the tie by index."""
+    bad = 0
+    for seed in range(40):
+        rng = np.random.default_rng(1000 + seed)
+        dist = small_case(rng)
+        lists = run_protocol(dist, 3, tile=32, rng=rng, in_order=False, max_lag=1)
+        bad += sum(lists[q] != brute_topk(dist[q], 3) for q in range(dist.shape[0]))
+    assert bad > 0
