@@ -14,6 +14,8 @@ from ._build import LIBPATH
 
 METRIC_HAMMING, METRIC_LEVEN = 0, 1
 MAX_L, MAX_K, MAX_PAM = 27, 32, 8
+MAX_BASES = 0xFFFFFF00          # gm_scan_create: uint32 coordinates
+MAX_INDEX = 1 << 27              # gm_index_create: 27-bit index in the (distance, index) key
 
 _c_i64p = ctypes.POINTER(ctypes.c_int64)
 _vp = ctypes.c_void_p
@@ -36,6 +38,20 @@ _SIGS = {
     "gm_gather_windows": [_vp, ctypes.c_int64, _vp, _vp, ctypes.c_int64, ctypes.c_int, _vp],
     "gm_seed_dedup": [_vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp],
     "gm_first_occurrence": [_vp, ctypes.c_int64, _vp],
+    "gm_seed_dedup_dev": [_vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp],
+    "gm_first_occurrence_dev": [_vp, ctypes.c_int64, _vp, _vp],
+    "gm_scan_device_ptrs": [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), _c_i64p],
+    "gm_session_create": [_vp, ctypes.c_int64, _vp, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                          ctypes.POINTER(_vp), _c_i64p],
+    "gm_session_info": [_vp, _c_i64p] + [ctypes.POINTER(ctypes.c_int)] * 4,
+    "gm_session_fetch_rows": [_vp, _vp, _vp, _vp, _vp, _vp],
+    "gm_session_fetch_text": [_vp, _vp, _vp, ctypes.c_int, _vp],
+    "gm_session_seed_dedup": [_vp, ctypes.c_int, _vp],
+    "gm_session_restriction": [_vp, _vp, _vp, ctypes.c_int, _vp],
+    "gm_session_index": [_vp, ctypes.c_int, ctypes.POINTER(_vp), _vp, _vp, _c_i64p],
+    "gm_session_knn": [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp],
+    "gm_session_knn_dev": [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp],
+    "gm_session_free": [_vp],
     "gm_restriction_scan": [_vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp],
     "gm_restriction_scan_dev": [_vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp],
     "gm_index_create": [_vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)],
@@ -148,6 +164,94 @@ def gather_windows(seq: np.ndarray, win_start: np.ndarray, revcomp: np.ndarray, 
     return out
 
 
+def _motif_tables(motifs):
+    motifs = list(motifs)
+    sets = np.zeros((max(len(motifs), 1), MAX_MOTIF), np.uint8)
+    lens = np.zeros(max(len(motifs), 1), np.int32)
+    for t, m in enumerate(motifs):
+        lens[t] = len(m)
+        for j, ch in enumerate(m[:MAX_MOTIF]):
+            sets[t, j] = IUPAC_SETS[ch]
+    return sets, lens, len(motifs)
+
+
+class Session:
+    """One genome scan whose rows (and the genome) stay in HBM; the later stages of the hot path run off this handle
+    (include/gm_b200.h, "session").  Records are joined by one invalid byte; ``rec_start[r]`` is the offset of record r
+    in ``buf`` and ``rec_start[-1] == len(buf) + 1``."""
+
+    def __init__(self, buf: np.ndarray, rec_start: np.ndarray, pam: str, five_prime: bool, L: int):
+        init()
+        self._h = _vp()
+        buf = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else np.ascontiguousarray(buf, np.uint8)
+        rec_start = np.ascontiguousarray(rec_start, np.int64)
+        n = ctypes.c_int64()
+        _check(load_library().gm_session_create(_p(buf) if len(buf) else None, len(buf), _p(rec_start), len(rec_start) - 1,
+                                                pam.encode("ascii", "replace"), len(pam), int(bool(five_prime)), int(L),
+                                                ctypes.byref(self._h), ctypes.byref(n)), "gm_session_create")
+        self.n_rows, self.L, self.P, self.five_prime = n.value, int(L), len(pam), bool(five_prime)
+
+    def fetch_rows(self):
+        """-> guide2bit u64[n], start u32[n] (record-relative), pamcode u16[n], rec i32[n], strand bool[n]"""
+        n = self.n_rows
+        g = np.empty(n, np.uint64); s = np.empty(n, np.uint32); p = np.empty(n, np.uint16); r = np.empty(n, np.int32); f = np.empty(n, np.uint8)
+        if n:
+            _check(load_library().gm_session_fetch_rows(self._h, _p(g), _p(s), _p(p), _p(r), _p(f)), "gm_session_fetch_rows")
+        return g, s, p, r, f.view(np.bool_)
+
+    def fetch_text(self, width: int = 30):
+        """-> target ASCII (n, L), context ASCII (n, width), edge bool[n] (context window leaves its record: row is '?')"""
+        n = self.n_rows
+        t = np.empty((n, self.L), np.uint8); c = np.empty((n, int(width)), np.uint8); e = np.empty(n, np.uint8)
+        if n:
+            _check(load_library().gm_session_fetch_text(self._h, _p(t), _p(c), int(width), _p(e)), "gm_session_fetch_text")
+        return t, c, e.view(np.bool_)
+
+    def seed_dedup(self, lsr: int) -> np.ndarray:
+        out = np.zeros(self.n_rows, np.uint8)
+        _check(load_library().gm_session_seed_dedup(self._h, int(lsr), _p(out)), "gm_session_seed_dedup")
+        return out.view(np.bool_)
+
+    def restriction(self, motifs) -> np.ndarray:
+        sets, lens, nm = _motif_tables(motifs)
+        out = np.zeros(self.n_rows, np.uint8)
+        _check(load_library().gm_session_restriction(self._h, _p(sets), _p(lens), nm, _p(out)), "gm_session_restriction")
+        return out.view(np.bool_)
+
+    def build_index(self, metric: int):
+        """-> (Index over the distinct guides, uniq u64[n_u] in first-occurrence order, row2uniq i32[n])"""
+        h, nu = _vp(), ctypes.c_int64()
+        uniq = np.empty(self.n_rows, np.uint64); r2u = np.empty(self.n_rows, np.int32)
+        _check(load_library().gm_session_index(self._h, int(metric), ctypes.byref(h), _p(uniq), _p(r2u), ctypes.byref(nu)), "gm_session_index")
+        return Index.from_handle(h, nu.value, self.L, metric), uniq[: nu.value].copy(), r2u
+
+    def knn(self, index: "Index", qmask: np.ndarray, k: int):
+        qmask = np.ascontiguousarray(qmask, np.uint8 if qmask.dtype != np.bool_ else np.bool_).view(np.uint8)
+        nq = int(np.count_nonzero(qmask))
+        idx = np.empty((nq, k), np.int32); dist = np.empty((nq, k), np.uint8)
+        _check(load_library().gm_session_knn(self._h, index._h, _p(qmask), nq, int(k), _p(idx), _p(dist)), "gm_session_knn")
+        return idx, dist
+
+    def knn_dev(self, index: "Index", qmask: np.ndarray, k: int, d_idx: int, d_dist: int, stream: int = 0) -> int:
+        """kNN of the masked rows into DEVICE buffers (no synchronisation); returns the number of query rows"""
+        qmask = np.ascontiguousarray(qmask, np.uint8 if qmask.dtype != np.bool_ else np.bool_).view(np.uint8)
+        nq = int(np.count_nonzero(qmask))
+        _check(load_library().gm_session_knn_dev(self._h, index._h, _p(qmask), nq, int(k), _vp(d_idx), _vp(d_dist), _vp(stream)),
+               "gm_session_knn_dev")
+        return nq
+
+    def close(self):
+        if self._h:
+            load_library().gm_session_free(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # ---- K2 ---------------------------------------------------------------------------------------------
 def seed_dedup(guides: np.ndarray, L: int, lsr: int, five_prime: bool) -> np.ndarray:
     init()
@@ -175,15 +279,9 @@ def restriction_scan(guides: np.ndarray, L: int, motifs) -> np.ndarray:
     """bool[n]: guide contains one of the IUPAC motifs (upper-case strings) at some offset (K6)."""
     init()
     guides = np.ascontiguousarray(guides, np.uint64)
-    motifs = list(motifs)
-    sets = np.zeros((max(len(motifs), 1), MAX_MOTIF), np.uint8)
-    lens = np.zeros(max(len(motifs), 1), np.int32)
-    for t, m in enumerate(motifs):
-        lens[t] = len(m)
-        for j, ch in enumerate(m[:MAX_MOTIF]):
-            sets[t, j] = IUPAC_SETS[ch]
+    sets, lens, nm = _motif_tables(motifs)
     out = np.zeros(len(guides), np.uint8)
-    _check(load_library().gm_restriction_scan(_p(guides), len(guides), int(L), _p(sets), _p(lens), len(motifs), _p(out)),
+    _check(load_library().gm_restriction_scan(_p(guides), len(guides), int(L), _p(sets), _p(lens), nm, _p(out)),
            "gm_restriction_scan")
     return out.view(np.bool_)
 
@@ -204,6 +302,13 @@ class Index:
         else:
             self.n = int(n)
             _check(lib.gm_index_create_dev(_vp(device_ptr), self.n, self.L, self.metric, ctypes.byref(self._h), _vp(stream)), "gm_index_create_dev")
+
+    @classmethod
+    def from_handle(cls, handle, n: int, L: int, metric: int) -> "Index":
+        """adopt an index handle created inside the library (gm_session_index)"""
+        self = cls.__new__(cls)
+        self._h, self.n, self.L, self.metric = handle, int(n), int(L), int(metric)
+        return self
 
     def knn(self, q2bit: np.ndarray, k: int, out_idx: np.ndarray | None = None, out_dist: np.ndarray | None = None):
         """host buffers in, host buffers out (synchronous); out_* may be caller-owned (e.g. pinned) arrays"""

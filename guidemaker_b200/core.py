@@ -39,7 +39,7 @@ import yaml
 from . import _capi
 from ._encode import as_byte_matrix, decode_matrix, encode_matrix, matrix_to_strings
 from .neighbors import ExactIndex, NeighborMap
-from .sharding import sharded_knn, sharded_min_dist
+from .sharding import broadcast_rank0, sharded_knn, sharded_min_dist, sharded_session_knn
 
 logger = logging.getLogger(__name__)
 
@@ -89,10 +89,10 @@ class _PackedStash:
     """Packed guides riding along in ``DataFrame.attrs``.  pandas deep-copies ``attrs`` into every Series/frame derived
     from the frame (``__finalize__``); the stash is immutable, so copies share it instead of duplicating 8 bytes per
     row on every column access."""
-    __slots__ = ("crc", "shape", "guides")
+    __slots__ = ("crc", "shape", "guides", "session")
 
-    def __init__(self, crc, shape, guides):
-        self.crc, self.shape, self.guides = crc, tuple(shape), guides
+    def __init__(self, crc, shape, guides, session=None):
+        self.crc, self.shape, self.guides, self.session = crc, tuple(shape), guides, session
         self.guides.setflags(write=False)
 
     def __deepcopy__(self, memo):
@@ -145,30 +145,29 @@ class PamTarget:
         buf = b"N".join(raw)
         if len(buf) == 0 and not raw:
             return pd.concat([])                     # the reference raises ValueError on no records
-        guides, gstart, pamcode, n_fwd, n_rev = _capi.pam_scan(buf, self.pam, five, L)
-        n = n_fwd + n_rev
+        if len(buf) > _capi.MAX_BASES:
+            raise ValueError("genome of %d bases exceeds the engine's uint32 coordinate range (%d); scan it in parts"
+                             % (len(buf), _capi.MAX_BASES))
+        # The scan keeps genome and rows in HBM (a "session"): rows come back already in the reference's order (per
+        # record forward hits, then reverse hits) with record-relative coordinates, and the two text columns are produced
+        # on the device from the resident data.  The later stages (seed flags, distinct guides, index, kNN) run off
+        # the same handle, which rides along in df.attrs.
+        sess = _capi.Session(np.frombuffer(buf, np.uint8), rec_start, self.pam, five, L)
+        n = sess.n_rows
         if n == 0:
             return pd.concat([])                     # zero hits -> ValueError (core.py:286-287)
-        strand = np.zeros(n, dtype=bool)
-        strand[:n_fwd] = True
-        rec = np.searchsorted(rec_start, gstart.astype(np.int64), side="right") - 1
-        if len(raw) > 1:                             # stable by record: forward block stays ahead of reverse block
-            order = np.argsort(rec, kind="stable")
-            guides, gstart, pamcode, strand, rec = guides[order], gstart[order], pamcode[order], strand[order], rec[order]
-        start = (gstart.astype(np.int64) - rec_start[rec])
-
-        seq30 = self._target_seq30(np.frombuffer(buf, np.uint8), seqs, rec, rec_start, lens, start, strand, five, P, L)
-        target_mat = decode_matrix(guides, L)
+        guides, start, pamcode, rec, strand = sess.fetch_rows()
+        target_mat, ctx, edge = sess.fetch_text(30)
+        seq30 = self._target_seq30(ctx, edge, seqs, rec, start, strand, five, P, L)
         df = pd.DataFrame({
             "target": _str_series(target_mat),
             "exact_pam": self._pam_categorical(pamcode, P),
-            "start": start.astype(np.uint32),
-            "stop": (start + L).astype(np.uint32),
+            "start": start,
+            "stop": start + np.uint32(L),
             "strand": strand,
             "pam_orientation": np.full(n, five, dtype=bool),
             "target_seq30": seq30,
-            "seqid": pd.Categorical.from_codes(rec, categories=pd.Index(ids).unique()) if len(set(ids)) == len(ids)
-            else pd.Categorical(np.asarray(ids, dtype=object)[rec]),
+            "seqid": self._seqid_categorical(ids, rec),
         })
         # seedseq=NaN -> 'str', hasrestrictionsite=NaN, isseedduplicated=NaN -> bool True, dtype -> category
         # (core.py:288-291), built directly instead of through astype
@@ -177,10 +176,23 @@ class PamTarget:
         df["hasrestrictionsite"] = np.nan
         df["isseedduplicated"] = True
         df["dtype"] = pd.Categorical.from_codes(np.zeros(n, dtype=np.int8), categories=[self.dtype])
-        # The packed guides ride along so that TargetProcessor need not re-encode n strings; they are used only if
-        # the CRC of the `target` column's bytes still matches (any edit, filter or reorder of the frame voids them).
-        df.attrs["_gm_packed"] = _PackedStash(zlib.crc32(target_mat), target_mat.shape, guides)
+        # The packed guides and the session ride along so that TargetProcessor need not re-encode / re-upload n strings;
+        # they are used only if the CRC of the `target` column's bytes still matches (any edit, filter or reorder of the
+        # frame voids them).
+        df.attrs["_gm_packed"] = _PackedStash(zlib.crc32(target_mat), target_mat.shape, guides, sess)
         return df
+
+    @staticmethod
+    def _seqid_categorical(ids, rec: np.ndarray) -> pd.Categorical:
+        """seqid as ``Series(strings).astype('category')`` would build it: categories in LEXICOGRAPHIC order, so that
+        ``export_bed``'s sort by chrom orders contigs as the reference does (its per-record concat degrades the column to
+        plain strings, which sort lexicographically) and not in FASTA record order."""
+        if len(set(ids)) != len(ids):
+            return pd.Categorical(np.asarray(ids, dtype=object)[rec])
+        order = sorted(range(len(ids)), key=lambda i: ids[i])
+        inv = np.empty(len(ids), dtype=np.int64)
+        inv[order] = np.arange(len(ids))
+        return pd.Categorical.from_codes(inv[rec], categories=pd.Index([ids[i] for i in order]))
 
     @staticmethod
     def _pam_categorical(pamcode: np.ndarray, P: int) -> pd.Categorical:
@@ -194,35 +206,28 @@ class PamTarget:
         return pd.Categorical.from_codes(lut[pamcode], categories=pd.Index([cats[i] for i in order], dtype="str"))
 
     @staticmethod
-    def _target_seq30(buf, seqs, rec, rec_start, lens, start, strand, five, P, L) -> pd.Series:
-        """The 30-nt context column (core.py:156,184,210-211,237): a Python slice of the record
-        around the match, reverse-complemented for reverse hits, NOT validated."""
+    def _target_seq30(ctx, edge, seqs, rec, start, strand, five, P, L) -> pd.Series:
+        """The 30-nt context column (core.py:156,184,210-211,237): a Python slice of the record around the match,
+        reverse-complemented for reverse hits, NOT validated.  `ctx` holds the device-gathered windows; rows flagged in
+        `edge` (window leaves the record) get the reference's literal slice semantics -- the piece may be shorter than 30
+        or empty."""
         n = len(start)
-        # match start/end on the forward text, from the target window (SURVEY Appendix A.1)
-        if five:
-            ms = np.where(strand, start - P, start + L)
-        else:
-            ms = np.where(strand, start + L, start - P)
-        me = ms + P
-        use_ms = strand == five                       # 5p fwd / 3p rev slice [ms-3, ms+27); others [me-27, me+3)
-        a = np.where(use_ms, ms - 3, me - 27)
-        interior = (a >= 0) & (a + 30 <= lens[rec])
-        # the gather (and the reverse complement of reverse-strand rows) runs on the GPU; rows whose window leaves
-        # their record are redirected outside the buffer and come back as '?'
-        out = _capi.gather_windows(buf, np.where(interior, a + rec_start[rec], -1), ~strand, 30)
-        if interior.all():
-            return _str_series(out)
-        # near record ends: literal Python slicing, as the reference -- the piece may be shorter than 30 or empty.
-        # The few exceptional rows are written left-aligned into the matrix and the column is assembled as ONE Arrow
-        # string array with per-row lengths (no detour through Python objects for the other rows).
+        rows = np.flatnonzero(edge)
+        if len(rows) == 0:
+            return _str_series(ctx)
+        # The few exceptional rows are spliced in and the column is assembled as ONE Arrow string array with per-row
+        # lengths (no detour through Python objects for the other rows).
         import pyarrow as pa
         width = np.full(n, 30, dtype=np.int64)
-        flat = out.reshape(-1)
+        flat = ctx.reshape(-1)
         parts, prev = [], 0
-        for i in np.flatnonzero(~interior):
-            s = seqs[rec[i]]
-            piece = s[int(a[i]): int(a[i]) + 30]
-            piece = (piece if strand[i] else _reverse_complement(piece)).encode("latin-1", "replace")
+        for i in rows:
+            st, fwd = int(start[i]), bool(strand[i])
+            # match start/end on the forward text, from the target window (SURVEY Appendix A.1)
+            ms = (st - P if fwd else st + L) if five else (st + L if fwd else st - P)
+            a = ms - 3 if fwd == five else ms + P - 27       # 5p fwd / 3p rev slice [ms-3, ms+27); others [me-27, me+3)
+            piece = seqs[rec[i]][a: a + 30]
+            piece = (piece if fwd else _reverse_complement(piece)).encode("latin-1", "replace")
             width[i] = len(piece)
             parts.append(flat[prev * 30: i * 30])     # the untouched rows before this one, as a view
             parts.append(np.frombuffer(piece, np.uint8))
@@ -278,11 +283,17 @@ class TargetProcessor:
             if (isinstance(stash, _PackedStash) and tuple(stash.shape) == mat.shape and len(stash.guides) == len(mat)
                     and stash.crc == zlib.crc32(np.ascontiguousarray(mat))):
                 guides = stash.guides                          # produced by find_targets for exactly these strings
+                sess = stash.session
             else:
-                guides = encode_matrix(mat)
-            cache = (key, guides, mat.shape[1], col.array)      # keep the array alive: ids stay unique
+                guides, sess = encode_matrix(mat), None
+            cache = (key, guides, mat.shape[1], col.array, sess)     # keep the array alive: ids stay unique
             self._packed_cache = cache
         return cache[1], cache[2]
+
+    def _session(self):
+        """the device-resident scan these rows came from (``find_targets``), or None if the frame was edited since"""
+        self._packed()
+        return self._packed_cache[4]
 
     # ---- reference API -------------------------------------------------------------------------------
     def check_restriction_enzymes(self, restriction_enzyme_list: list = []) -> None:
@@ -298,7 +309,8 @@ class TargetProcessor:
             motifs.append(_reverse_complement(record.upper()))
         if len(motifs) > 0:
             guides, L = self._packed()
-            self.targets['hasrestrictionsite'] = _capi.restriction_scan(guides, L, motifs)
+            sess = self._session()
+            self.targets['hasrestrictionsite'] = sess.restriction(motifs) if sess is not None else _capi.restriction_scan(guides, L, motifs)
         else:
             self.targets['hasrestrictionsite'] = False
 
@@ -309,8 +321,9 @@ class TargetProcessor:
 
     def find_unique_near_pam(self) -> None:
         """seedseq = PAM-proximal ``lsr`` nt; isseedduplicated = keep-first duplicate flag (core.py:388-416)."""
-        self.targets = deepcopy(self.targets)
         guides, _ = self._packed()
+        sess = self._session()
+        self.targets = deepcopy(self.targets)
         mat = self._guide_matrix()
         L = mat.shape[1]
         five = bool(self.pam_orientation)
@@ -325,9 +338,10 @@ class TargetProcessor:
                 cut = max(L + cut, 0)
             seed, lsr_eff = mat[:, cut:], L - cut
         self.targets['seedseq'] = _str_series(np.ascontiguousarray(seed), index=self.targets.index)
-        self.targets['isseedduplicated'] = _capi.seed_dedup(guides, L, lsr_eff if lsr_eff < L else 0, five)
+        lsr_key = lsr_eff if lsr_eff < L else 0
+        self.targets['isseedduplicated'] = sess.seed_dedup(lsr_key) if sess is not None else _capi.seed_dedup(guides, L, lsr_key, five)
         col = self.targets['target']
-        self._packed_cache = ((id(self.targets), id(col.array), len(col)), guides, L, col.array)
+        self._packed_cache = ((id(self.targets), id(col.array), len(col)), guides, L, col.array, sess)
 
     def create_index(self, configpath: str, num_threads=2):
         """Upload the distinct guides to the GPU (replaces the HNSW build, core.py:418-467).
@@ -338,13 +352,23 @@ class TargetProcessor:
             config = yaml.safe_load(cf)
         M, efC, post = config['NMSLIB']['M'], config['NMSLIB']['efc'], config['NMSLIB']['post']  # noqa: F841
         guides, L = self._packed()
-        first_row = _capi.first_occurrence(guides)
-        is_first = first_row == np.arange(len(guides))
-        uniq = np.ascontiguousarray(guides[is_first])
+        sess = self._session()
         metric = _capi.METRIC_HAMMING if self._is_hamming() else _capi.METRIC_LEVEN
-        self.nmslib_index = ExactIndex(uniq, L, metric)
+        if sess is not None:                                   # distinct guides, index and row map built on the device
+            engine, uniq, row2uniq = sess.build_index(metric)
+            self.nmslib_index = ExactIndex(uniq, L, metric, engine=engine)
+            self._index_session = sess
+        else:
+            first_row = _capi.first_occurrence(guides)
+            is_first = first_row == np.arange(len(guides))
+            uniq = np.ascontiguousarray(guides[is_first])
+            if len(uniq) >= _capi.MAX_INDEX:
+                raise ValueError("%d distinct guides exceed the engine's limit of 2^27 - 1 per index" % len(uniq))
+            self.nmslib_index = ExactIndex(uniq, L, metric)
+            row2uniq = (np.cumsum(is_first, dtype=np.int64) - 1)[first_row]
+            self._index_session = None
         # row -> index of its guide in the distinct-guide table (valid while the packed cache is)
-        self._row2uniq = (self._packed_cache[0], (np.cumsum(is_first, dtype=np.int64) - 1)[first_row])
+        self._row2uniq = (self._packed_cache[0], row2uniq)
 
     def get_neighbors(self, configpath, num_threads=2) -> None:
         """k nearest guides of every query row; keep a query iff its nearest OTHER guide is at least
@@ -355,13 +379,17 @@ class TargetProcessor:
         t = self.targets
         qmask = ((t['isseedduplicated'] == False) | (t['hasrestrictionsite'] == False)).to_numpy(dtype=bool)  # noqa: E712
         guides, L = self._packed()
+        sess = self._session()
         q = np.ascontiguousarray(guides[qmask])
         index = self.nmslib_index
         index.setQueryTimeParams({'efSearch': ef})
         if len(q) == 0:
             self.neighbors = NeighborMap(q, np.zeros((0, self.knum), np.int32), np.zeros((0, self.knum), np.uint8), index.uniq, L)
             return
-        idx, dist = sharded_knn(index, q, int(self.knum))
+        if sess is not None and hasattr(index._engine, "_h"):  # queries are compacted on the device from the resident rows
+            idx, dist = sharded_session_knn(sess, index._engine, qmask, int(self.knum))
+        else:
+            idx, dist = sharded_knn(index, q, int(self.knum))
         if dist.shape[1] < 2 or (idx[:, 1] < 0).any():
             raise IndexError("list index out of range")    # editdist[1] with fewer than 2 hits (core.py:512,518)
         rows = np.flatnonzero(dist[:, 1] >= int(self.editdist))           # kept query rows (core.py:518)
@@ -426,6 +454,9 @@ class TargetProcessor:
                     u = np.random.random_sample((hi - lo, length))
                     sel = letter_code[np.searchsorted(cdf, u, side="right")]
                     codes[lo:hi] = np.bitwise_or.reduce(sel << shifts, axis=1)
+                    # multi-rank: every rank must search the SAME candidates (the global numpy RNG is per process and
+                    # not necessarily seeded alike) -- rank 0's draw is authoritative
+                    codes[lo:hi] = broadcast_rank0(codes[lo:hi])
                     dist[lo:hi] = sharded_min_dist(index, codes[lo:hi])
                 order = np.argsort(-dist.astype(np.int64), kind="stable")[:n]   # descending, ties in draw order
                 sort_codes = codes[order]

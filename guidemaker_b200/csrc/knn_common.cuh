@@ -77,6 +77,7 @@ __device__ __forceinline__ void issue_chunk(uint2 *dst, const uint2 *src, uint64
 int launch_hamming_tc(dim3 grid, cudaStream_t st, const ScanArgs &a);
 int tc_permute_planes(const uint2 *planes, int64_t n, uint2 *out, cudaStream_t st);
 int tc_query_tile();
+int tc_k_chunks(int L);
 int microbench_mma_i8(int variant, double *ops_per_s);
 
 }  // namespace gm

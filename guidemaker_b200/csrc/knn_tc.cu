@@ -1,10 +1,15 @@
 // knn_tc.cu -- K3b: exact Hamming kNN as a one-hot int8 GEMM on the 5th-gen tensor cores (sm_100a).
 //
-// Hamming(q, t) = L - <onehot(q), onehot(t)>.  A CTA owns 512 queries as two A operands ("sets") of 128 rows, TWO
-// queries per row with weights 1 and 64 (bytes <= 65), K = 4 bytes per base position (+ one 16-byte chunk that
-// carries per-row bias bytes).  Targets stream through shared memory as the B operand, expanded on the fly from
-// their 8-byte bit planes to one-hot int8 rows.  One `tcgen05.mma.cta_group::1.kind::i8` is M=128 x N=128 x K=32;
-// the int32 accumulator of (row r, target n) in TMEM is
+// Hamming(q, t) = L - m(q, t), m = number of matching positions, and m is a genuine dense contraction.  The encoding
+// is the rank-minimal one (the 4 x 4 "same base" matrix needs three dimensions plus a constant):
+//        target base  ->  g = ([t=C], [t=G], [t=T])                      pure 0/1 bytes (the hot, per-tile expansion)
+//        query base   ->  f = ([q=C]-[q=A], [q=G]-[q=A], [q=T]-[q=A])     bytes in {-1, 0, 1}
+//        <f(q), g(t)> = [q=t] - [q=A]   =>   sum over positions = m - countA(q),
+// and countA(q) is a per-query constant that is folded into the query's bias byte.  THREE bytes per base position
+// instead of the four of a one-hot row: a 20-nt guide is 60 bytes + 2 bias bytes = TWO 32-byte MMA K steps, not three.
+// A CTA owns 512 queries as two A operands ("sets") of 128 rows, TWO queries per row with weights 1 and 64 (bytes in
+// [-65, 65]).  Targets stream through shared memory as the B operand, expanded on the fly from their 8-byte bit planes.
+// One `tcgen05.mma.cta_group::1.kind::i8` is M=128 x N=128 x K=32; the int32 accumulator of (row r, target n) in TMEM is
 //        (m1 + b1) + 64 * (m2 + b2),      m_i = matching positions of query i,  b_i = 31 - L + tau_i,
 // so bit 5 / bit 11 is set iff query 1 / 2 of the row is closer to the target than its current bound tau_i (the
 // distance of its k-th best so far).  The accumulator is ONLY a filter: the epilogue warps read it back with
@@ -42,10 +47,12 @@
 //                into the bias byte of A, where later MMAs pick it up.  Idle candidate warps poll every 2 us: every
 //                poll costs shared-memory cycles.
 //
-// Bit order.  The one-hot rows need byte m of word (chunk j, base b) = [base at position 4j+m is b].  The index keeps
-// a second copy of the planes with position p stored at bit (p>>2) + 8(p&3): then that word is (mask_b >> j) &
-// 0x01010101 -- two instructions per four bytes.  Hamming distance is invariant under a common bit permutation, so the
-// candidate warps work on the permuted planes too (queries are permuted once per CTA).
+// K layout.  A row of K bytes is a string of 32-bit words: word 3g + x holds, for the four positions 4g .. 4g+3, the
+// bytes of base x (0 = C, 1 = G, 2 = T); the LAST word of the row carries the bias bytes (A side: b1, b2; B side: 1, 64).
+// The index keeps a second copy of the planes with position p stored at bit (p>>2) + 8(p&3): then word (g, x) of a
+// target is (mask_x >> g) & 0x01010101 -- two instructions per four bytes.  Hamming distance is invariant under a common
+// bit permutation, so the candidate warps work on the permuted planes too (queries are permuted once per CTA).
+
 #include "knn_common.cuh"
 
 namespace gm {
@@ -81,6 +88,12 @@ static_assert(TC_THREADS <= 1024 && TC_EPI_WARPS * 32 == TC_QT, "one epilogue th
 static constexpr uint32_t TC_FLAGS = 0x08200820u;   // bit 5 / bit 11 of both 16-bit halves of a packed register
 
 int tc_query_tile() { return TC_QT; }
+// 16-byte K chunks per row: 3 words per group of four positions + the bias word, rounded up to whole 32-byte MMA K steps
+// (L <= 8: 2, L <= 20: 4, L <= 27: 6)
+int tc_k_chunks(int L) {
+    const int words = 3 * ((L + 3) / 4) + 1;
+    return (((words + 3) / 4) + 1) & ~1;
+}
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_alloc(uint32_t *dst_smem, uint32_t cols) {
@@ -150,9 +163,10 @@ int tc_permute_planes(const uint2 *planes, int64_t n, uint2 *out, cudaStream_t s
     return GM_OK;
 }
 
-// one 16-byte K chunk from permuted masks: positions 4j..4j+3, words = bases A, C, G, T
-__device__ __forceinline__ uint4 onehot_chunk(uint32_t eA, uint32_t eC, uint32_t eG, uint32_t eT, int j) {
-    return make_uint4((eA >> j) & 0x01010101u, (eC >> j) & 0x01010101u, (eG >> j) & 0x01010101u, (eT >> j) & 0x01010101u);
+// word w (< 3 * groups) of a K row from the permuted base masks e[0..2] = C, G, T: base w % 3 of positions 4g .. 4g+3,
+// g = w / 3.  w is a compile-time constant at every call site (unrolled loops).
+__device__ __forceinline__ uint32_t k_word(const uint32_t (&e)[3], int w) {
+    return (e[w % 3] >> (w / 3)) & 0x01010101u;
 }
 
 // a spin loop outlived ~10 s: fail the launch instead of hanging the GPU (1 = issue order, 2 = candidate queue, 3 = mbarrier)
@@ -206,8 +220,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = a.L;
-    const int nd = (L + 3) >> 2;                      // data chunks 0 .. nd-1 (nd < kc)
-    constexpr int kb = kc - 1;                        // the LAST chunk carries the bias bytes: a compile-time position
+    constexpr int kwords = 4 * kc;                    // 32-bit words per K row; data words 0 .. 3*ceil(L/4)-1 (< kwords - 1)
+    constexpr int kb = kc - 1;                        // the LAST word of the LAST chunk carries the bias bytes: a compile-time position
     const uint32_t lmask = tc_permute_bits((1u << L) - 1u);
     const uint32_t a_bytes = (uint32_t)TC_M * 16u * (uint32_t)kc;
     const uint32_t b_bytes = (uint32_t)TC_N * 16u * (uint32_t)kc;
@@ -266,25 +280,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
     // ---- A tiles: set s, row r = query (256 s + r) * 1 + query (256 s + 128 + r) * 64 ------------------------------
     if (tid < TC_SETS * TC_M) {
         const int set = tid >> 7, row = tid & 127;
-        uint32_t e[2][4], tau[2];
+        uint32_t e[2][3], eA[2], tau[2];
 #pragma unroll
         for (int s = 0; s < 2; s++) {
             const uint2 p = sQ[(set * 128 + row) * 2 + s];
             tau[s] = sBound[(set * 128 + row) * 2 + s] >> IDX_BITS;
-            e[s][0] = ~(p.x | p.y) & lmask; e[s][1] = p.x & ~p.y; e[s][2] = p.y & ~p.x; e[s][3] = p.x & p.y;
+            eA[s] = ~(p.x | p.y) & lmask; e[s][0] = p.x & ~p.y; e[s][1] = p.y & ~p.x; e[s][2] = p.x & p.y;
         }
         uint8_t *myA = sA + (size_t)set * a_bytes;
 #pragma unroll
         for (int j = 0; j < kc; j++) {
-            uint4 w = make_uint4(0u, 0u, 0u, 0u);
-            if (j < nd) {
-                const uint4 w0 = onehot_chunk(e[0][0], e[0][1], e[0][2], e[0][3], j);
-                const uint4 w1 = onehot_chunk(e[1][0], e[1][1], e[1][2], e[1][3], j);
-                w = make_uint4(w0.x + 64u * w1.x, w0.y + 64u * w1.y, w0.z + 64u * w1.z, w0.w + 64u * w1.w);
-            } else if (j == kb) {
-                w.x = (uint32_t)(31 - L + (int)tau[0]) | ((uint32_t)(31 - L + (int)tau[1]) << 8);
+            uint32_t w[4];
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                const int wi = 4 * j + x;
+                if (wi == kwords - 1) {
+                    // bias bytes: 31 - L + tau + countA(query) (the data words sum to m - countA)
+                    w[x] = (uint32_t)(31 - L + (int)tau[0] + __popc(eA[0])) | ((uint32_t)(31 - L + (int)tau[1] + __popc(eA[1])) << 8);
+                } else {
+                    // per byte: ([q1 = base] - [q1 = A]) + 64 ([q2 = base] - [q2 = A]), two's complement, no carries between bytes
+                    const uint32_t a0 = (eA[0] >> (wi / 3)) & 0x01010101u, a1 = (eA[1] >> (wi / 3)) & 0x01010101u;
+                    w[x] = __vsub4(k_word(e[0], wi) + (k_word(e[1], wi) << 6), a0 + (a1 << 6));
+                }
             }
-            *reinterpret_cast<uint4 *>(myA + (size_t)j * (TC_M * 16) + (size_t)row * 16) = w;
+            *reinterpret_cast<uint4 *>(myA + (size_t)j * (TC_M * 16) + (size_t)row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
         }
         fence_async_smem();
     }
@@ -390,13 +409,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
             const uint32_t round = (uint32_t)(i / TC_STAGES);
             const uint2 tp = tnext;
             if (i + 2 < n_tiles) tnext = tsrc[(size_t)(i + 2) * TC_N];       // prefetch this thread's next target
-            const uint32_t eA = ~(tp.x | tp.y) & lmask, eC = tp.x & ~tp.y, eG = tp.y & ~tp.x, eT = tp.x & tp.y;
+            const uint32_t e[3] = {tp.x & ~tp.y, tp.y & ~tp.x, tp.x & tp.y};     // C, G, T (an A is three zero bytes)
             if (round > 0 && !(GM_TC_ABL & 32)) tc_wait(&b_empty[s], (round - 1) & 1u);
             uint8_t *dstp = sB + (size_t)s * b_bytes + (size_t)p * 16;
 #pragma unroll
             for (int j = 0; j < ((GM_TC_ABL & 2) ? 0 : kc); j++) {  // positions beyond L have all-zero masks
-                uint4 w = onehot_chunk(eA, eC, eG, eT, j);
-                if (j == kb) w.x = 1u | (64u << 8);                 // multiplies the bias bytes of A: 1 * b1 + 64 * b2
+                uint4 w = make_uint4(k_word(e, 4 * j), k_word(e, 4 * j + 1), k_word(e, 4 * j + 2), k_word(e, 4 * j + 3));
+                if (j == kb) w.w = 1u | (64u << 8);                 // multiplies the bias bytes of A: 1 * b1 + 64 * b2
                 *reinterpret_cast<uint4 *>(dstp + j * (TC_N * 16)) = w;
             }
             if (!(GM_TC_ABL & 16)) fence_async_smem();              // generic-proxy writes -> visible to the tensor core
@@ -504,8 +523,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
                         // tighten the bias byte; later MMAs pick it up.  No proxy fence: the byte only has to reach the
                         // tensor core eventually (measured: the fence changes nothing)
                         if ((bound >> IDX_BITS) != (bound0 >> IDX_BITS))
-                            sA[(size_t)set * a_bytes + (size_t)kb * (TC_M * 16) + (size_t)row * 16 + e] =
-                                (uint8_t)(31 - L + (int)(bound >> IDX_BITS));
+                            sA[(size_t)set * a_bytes + (size_t)kb * (TC_M * 16) + (size_t)row * 16 + 12 + e] =
+                                (uint8_t)(31 - L + (int)(bound >> IDX_BITS) + __popc(~((e ? qq.z : qq.x) | (e ? qq.w : qq.y)) & lmask));
                     }
                     __syncwarp();
                 }
@@ -684,13 +703,10 @@ static int launch_tc_kc(dim3 grid, cudaStream_t st, const ScanArgs &a) {
 }
 
 int launch_hamming_tc(dim3 grid, cudaStream_t st, const ScanArgs &a) {
-    const int nd = (a.L + 3) / 4;
-    const int kc = ((nd + 1) + 1) & ~1;         // data chunks + bias chunk, rounded up to whole 32-byte MMA K steps
-    switch (kc) {
+    switch (tc_k_chunks(a.L)) {
     case 2: return launch_tc_kc<2>(grid, st, a);
     case 4: return launch_tc_kc<4>(grid, st, a);
-    case 6: return launch_tc_kc<6>(grid, st, a);
-    default: return launch_tc_kc<8>(grid, st, a);
+    default: return launch_tc_kc<6>(grid, st, a);
     }
 }
 

@@ -19,19 +19,12 @@
 //                  reverse-strand guides are reverse-complemented with brev + bitwise not.
 //
 // Algorithmic HBM bytes: n (ASCII in) + 3n/8 (planes out) + 2 * 3n/8 (planes in, twice) + 14 B per hit.
-#include "common.cuh"
+#include "scan.cuh"
 #include <new>
 
 namespace gm {
 
 static constexpr int SCAN_THREADS = 256;
-
-struct Scan {
-    uint64_t *guides = nullptr;
-    uint32_t *start = nullptr;
-    uint16_t *pamcode = nullptr;
-    int64_t n_fwd = 0, n_rev = 0;
-};
 
 struct PamParams {
     int P, L, five_prime;
@@ -254,33 +247,184 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_emit_kernel(const PamParams
     }
 }
 
-}  // namespace gm
 
-using namespace gm;
+// ---- record-ordered emit (sessions) -----------------------------------------------------------------------------------
+// The reference lists, PER RECORD, all forward hits and then all reverse hits (core.py:254-284).  With the global
+// forward / reverse ranks of a hit (gf, gr: its position among all forward / reverse hits of the joined genome) and the
+// ranks F[r], R[r] of the first position of record r, the row of a hit of record r is
+//      forward:  F[r] + R[r] + (gf - F[r])                      = R[r] + gf
+//      reverse:  F[r] + R[r] + (F[r+1] - F[r]) + (gr - R[r])    = F[r+1] + gr
+// so the scan writes every row straight to its final place -- no sort, no regrouping on the host.
 
-extern "C" int gm_scan_free(void *scan) {
-    Scan *s = (Scan *)scan;
-    if (!s) return GM_OK;
-    dev_free(s->guides, 0);
-    dev_free(s->start, 0);
-    dev_free(s->pamcode, 0);
-    delete s;
+// ranks at the record boundaries: one CTA per boundary r (1 <= r < n_rec) counts the hits of its block before rec_start[r]
+__global__ void __launch_bounds__(SCAN_THREADS) boundary_rank_kernel(const PamParams pp, int64_t n_words, const uint32_t *__restrict__ lo,
+                                                                     const uint32_t *__restrict__ hi, const uint32_t *__restrict__ valid,
+                                                                     const uint64_t *__restrict__ off_f, const uint64_t *__restrict__ off_r,
+                                                                     const uint64_t *__restrict__ totals, const int64_t *__restrict__ rec_start,
+                                                                     int n_rec, uint64_t *__restrict__ F, uint64_t *__restrict__ R) {
+    __shared__ uint32_t s_f[SCAN_THREADS / 32], s_r[SCAN_THREADS / 32];
+    const int r = blockIdx.x;                              // 0 .. n_rec
+    if (r == 0) { if (threadIdx.x == 0) { F[0] = 0; R[0] = 0; } return; }
+    const int64_t b = rec_start[r];
+    const int64_t wb = b >> 5;
+    if (r == n_rec || wb >= n_words) { if (threadIdx.x == 0) { F[r] = totals[0]; R[r] = totals[1]; } return; }
+    const int64_t blk = wb / SCAN_THREADS;
+    const int64_t w = blk * SCAN_THREADS + threadIdx.x;
+    uint32_t cf = 0, cr = 0;
+    if (w <= wb) {
+        uint32_t hf, hr;
+        hit_words(pp, load_win(lo, w), load_win(hi, w), load_win(valid, w), hf, hr);
+        if (w == wb) { const uint32_t m = (1u << (b & 31)) - 1u; hf &= m; hr &= m; }
+        cf = __popc(hf);
+        cr = __popc(hr);
+    }
+    cf = __reduce_add_sync(0xFFFFFFFFu, cf);
+    cr = __reduce_add_sync(0xFFFFFFFFu, cr);
+    if ((threadIdx.x & 31) == 0) { s_f[threadIdx.x >> 5] = cf; s_r[threadIdx.x >> 5] = cr; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t tf = 0, tr = 0;
+        for (int i = 0; i < SCAN_THREADS / 32; i++) { tf += s_f[i]; tr += s_r[i]; }
+        F[r] = off_f[blk] + tf;
+        R[r] = off_r[blk] + tr;
+    }
+}
+
+__device__ __forceinline__ int record_of(const int64_t *__restrict__ rec_start, int n_rec, int64_t pos) {
+    int lo = 0, hi = n_rec;                                // largest r with rec_start[r] <= pos
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (rec_start[mid] <= pos) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_emit_records_kernel(const PamParams pp, int64_t n_words,
+                                                                         const uint32_t *__restrict__ lo, const uint32_t *__restrict__ hi,
+                                                                         const uint32_t *__restrict__ valid,
+                                                                         const uint64_t *__restrict__ off_f, const uint64_t *__restrict__ off_r,
+                                                                         const int64_t *__restrict__ rec_start, int n_rec,
+                                                                         const uint64_t *__restrict__ F, const uint64_t *__restrict__ R,
+                                                                         uint64_t *__restrict__ guides, uint32_t *__restrict__ start,
+                                                                         uint16_t *__restrict__ pamcode, int32_t *__restrict__ rec,
+                                                                         uint8_t *__restrict__ strand) {
+    __shared__ uint32_t s_f[SCAN_THREADS / 32], s_r[SCAN_THREADS / 32];
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t hf = 0, hr = 0;
+    Win wl, wh;
+    wl.x0 = wl.x1 = wl.x2 = wl.x3 = 0;
+    wh = wl;
+    if (w < n_words) {
+        wl = load_win(lo, w);
+        wh = load_win(hi, w);
+        hit_words(pp, wl, wh, load_win(valid, w), hf, hr);
+    }
+    const uint32_t cf = __popc(hf), cr = __popc(hr);
+    uint32_t sf = cf, sr = cr;                       // inclusive warp scans
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t tf = __shfl_up_sync(0xFFFFFFFFu, sf, d), tr = __shfl_up_sync(0xFFFFFFFFu, sr, d);
+        if (lane >= d) { sf += tf; sr += tr; }
+    }
+    if (lane == 31) { s_f[warp] = sf; s_r[warp] = sr; }
+    __syncthreads();
+    if ((hf | hr) == 0u) return;
+    uint32_t wf = 0, wr = 0;
+    for (int i = 0; i < warp; i++) { wf += s_f[i]; wr += s_r[i]; }
+    uint64_t gf = off_f[blockIdx.x] + wf + sf - cf;   // global forward / reverse rank of this word's first hit
+    uint64_t gr = off_r[blockIdx.x] + wr + sr - cr;
+
+    const uint32_t lmask = (1u << pp.L) - 1u, pmask = (1u << pp.P) - 1u;
+    const int64_t pos0 = w * 32;
+    const int r0 = record_of(rec_start, n_rec, pos0);
+    int r = r0;
+    while (hf) {                                     // forward-strand rows, ascending position
+        const int b = __ffs(hf) - 1;
+        hf &= hf - 1;
+        while (pos0 + b >= rec_start[r + 1]) r++;
+        const uint64_t o = R[r] + gf;
+        const uint32_t gl = wl.at(b + pp.off_f) & lmask, gh = wh.at(b + pp.off_f) & lmask;
+        const uint32_t pl = wl.at(b) & pmask, ph = wh.at(b) & pmask;
+        guides[o] = from_planes(gl, gh);
+        start[o] = (uint32_t)(pos0 + b + pp.off_f - rec_start[r]);
+        pamcode[o] = (uint16_t)from_planes(pl, ph);
+        rec[o] = r;
+        strand[o] = 1;
+        gf++;
+    }
+    r = r0;
+    while (hr) {                                     // reverse-strand rows: reverse complement
+        const int b = __ffs(hr) - 1;
+        hr &= hr - 1;
+        while (pos0 + b >= rec_start[r + 1]) r++;
+        const uint64_t o = F[r + 1] + gr;
+        const uint32_t gl = bit_reverse_low(~wl.at(b + pp.off_r) & lmask, pp.L);
+        const uint32_t gh = bit_reverse_low(~wh.at(b + pp.off_r) & lmask, pp.L);
+        const uint32_t pl = bit_reverse_low(~wl.at(b) & pmask, pp.P);
+        const uint32_t ph = bit_reverse_low(~wh.at(b) & pmask, pp.P);
+        guides[o] = from_planes(gl, gh);
+        start[o] = (uint32_t)(pos0 + b + pp.off_r - rec_start[r]);
+        pamcode[o] = (uint16_t)from_planes(pl, ph);
+        rec[o] = r;
+        strand[o] = 0;
+        gr++;
+    }
+}
+
+// ---- text columns of the frame, produced from the resident rows and genome ---------------------------------------------
+// `target` (core.py:155,183,209,236): the guide as ASCII, L bytes per row.
+__global__ void __launch_bounds__(256) decode_rows_kernel(const uint64_t *__restrict__ guides, int64_t n_rows, int L, uint8_t *__restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_rows * L) return;
+    const int64_t i = t / L;
+    const int j = (int)(t - i * L);
+    out[t] = (uint8_t)("ACGT"[(guides[i] >> (2 * j)) & 3u]);
+}
+
+__constant__ uint8_t c_comp[256];
+
+// `target_seq30` (core.py:156,184,210-211,237): the 30-nt slice of the record around the match -- [ms-3, ms+27) for 5prime
+// forward / 3prime reverse hits, [me-27, me+3) for the others -- reverse-complemented for reverse hits, NOT validated.
+// Rows whose window leaves the record are flagged in `edge` and filled with '?': the host applies Python's literal slice
+// semantics to those few rows.
+__global__ void __launch_bounds__(256) context_rows_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ rec_start,
+                                                           const uint32_t *__restrict__ start, const int32_t *__restrict__ rec,
+                                                           const uint8_t *__restrict__ strand, int64_t n_rows, int P, int L,
+                                                           int five_prime, int width, uint8_t *__restrict__ out, uint8_t *__restrict__ edge) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_rows * width) return;
+    const int64_t i = t / width;
+    const int j = (int)(t - i * width);
+    const int r = rec[i];
+    const int fwd = strand[i];
+    const int64_t st = start[i];
+    const int64_t ms = five_prime ? (fwd ? st - P : st + L) : (fwd ? st + L : st - P);
+    const int64_t a = (fwd == five_prime) ? ms - 3 : ms + P - (width - 3);
+    const int64_t len = rec_start[r + 1] - rec_start[r] - 1;
+    const bool interior = a >= 0 && a + width <= len;
+    uint8_t c = (uint8_t)'?';
+    if (interior) {
+        const int64_t g0 = rec_start[r] + a;
+        c = fwd ? seq[g0 + j] : c_comp[seq[g0 + width - 1 - j]];
+    }
+    out[t] = c;
+    if (j == 0 && edge) edge[i] = interior ? 0 : 1;
+}
+
+static int ensure_comp_table() {
+    static bool table_set = false;
+    if (!table_set) {
+        uint8_t comp[256];
+        for (int c = 0; c < 256; c++) comp[c] = (uint8_t)c;
+        const char *from = "ACGTMRWSYKVHDBXNacgtmrwsykvhdbxn", *to = "TGCAKYWSRMBDHVXNtgcakywsrmbdhvxn";   // Bio.Seq complement
+        for (int k = 0; from[k]; k++) comp[(uint8_t)from[k]] = (uint8_t)to[k];
+        GM_CUDA(cudaMemcpyToSymbol(c_comp, comp, 256));
+        table_set = true;
+    }
     return GM_OK;
 }
 
-extern "C" int gm_scan_create(const uint8_t *seq_ascii, int64_t n, const char *pam, int pam_len, int five_prime, int L,
-                              void **scan, int64_t *n_fwd, int64_t *n_rev) {
-    int rc = ensure_init();
-    if (rc) return rc;
-    GM_ARG(scan && n_fwd && n_rev, "gm_scan_create: NULL output pointer");
-    *scan = nullptr;
-    *n_fwd = *n_rev = 0;
-    GM_ARG(n >= 0 && (n == 0 || seq_ascii), "gm_scan_create: bad sequence buffer");
-    GM_ARG(pam && pam_len >= 1 && pam_len <= GM_MAX_PAM, "gm_scan_create: PAM length %d outside [1,%d]", pam_len, GM_MAX_PAM);
-    GM_ARG(L >= 1 && L <= GM_MAX_L, "gm_scan_create: L=%d outside [1,%d]", L, GM_MAX_L);
-    if (n > 0xFFFFFF00LL) { set_error("gm_scan_create: %lld bases exceed the uint32 coordinate range", (long long)n); return GM_ERR_RANGE; }
-
-    PamParams pp;
+static int fill_params(PamParams &pp, const char *pam, int pam_len, int five_prime, int L) {
     memset(&pp, 0, sizeof pp);
     pp.P = pam_len;
     pp.L = L;
@@ -293,26 +437,33 @@ extern "C" int gm_scan_create(const uint8_t *seq_ascii, int64_t n, const char *p
     // target window relative to the match start ms (me = ms + P): core.py:155,183,209,236
     pp.off_f = five_prime ? pam_len : -L;
     pp.off_r = five_prime ? -L : pam_len;
+    return GM_OK;
+}
 
-    Scan *s = new (std::nothrow) Scan();
-    if (!s) { set_error("out of host memory"); return GM_ERR_NOMEM; }
-    *scan = s;
-    if (n == 0) return GM_OK;
-
+// Everything of a scan: upload, encode, count, offsets, emit.  Plain scans (rec_start == nullptr) list all forward rows
+// and then all reverse rows with genome-wide coordinates; sessions list rows per record and keep the genome resident.
+static int scan_build(Scan *s, const uint8_t *seq_ascii, int64_t n, const PamParams &pp, const int64_t *rec_start, int n_rec) {
     const int64_t n_words = (n + 31) / 32;
     const int64_t n_blocks = (n_words + SCAN_THREADS - 1) / SCAN_THREADS;
     const size_t plane_words = (size_t)n_words + 4;
+    const bool session = rec_start != nullptr;
     uint8_t *d_seq = nullptr;
     uint32_t *d_planes = nullptr, *d_blk = nullptr;
-    uint64_t *d_off = nullptr;
+    uint64_t *d_off = nullptr, *d_FR = nullptr;
     uint64_t totals[2] = {0, 0};
+    const double t0 = now_ms();
     cudaError_t e = dev_alloc((void **)&d_seq, (size_t)n_words * 32, 0);
     if (e == cudaSuccess) e = dev_alloc((void **)&d_planes, 3 * plane_words * 4, 0);
     if (e == cudaSuccess) e = dev_alloc((void **)&d_blk, (size_t)n_blocks * 2 * 4, 0);
     if (e == cudaSuccess) e = dev_alloc((void **)&d_off, ((size_t)n_blocks * 2 + 2) * 8, 0);
-    if (e == cudaSuccess) e = cudaMemset(d_seq + (n_words - 1) * 32, 0, 32);
-    if (e == cudaSuccess) e = cudaMemcpy(d_seq, seq_ascii, (size_t)n, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemset(d_planes, 0, 3 * plane_words * 4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_seq + (n_words - 1) * 32, 0, 32, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_seq, seq_ascii, (size_t)n, cudaMemcpyHostToDevice, 0);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_planes, 0, 3 * plane_words * 4, 0);
+    if (e == cudaSuccess && session) {
+        e = dev_alloc((void **)&s->rec_start, (size_t)(n_rec + 1) * 8, 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->rec_start, rec_start, (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, 0);
+        if (e == cudaSuccess) e = dev_alloc((void **)&d_FR, (size_t)(n_rec + 1) * 2 * 8, 0);
+    }
     uint32_t *lo = d_planes, *hi = d_planes + plane_words, *va = d_planes + 2 * plane_words;
     uint32_t *blk_f = d_blk, *blk_r = d_blk + n_blocks;
     uint64_t *off_f = d_off, *off_r = d_off + n_blocks, *d_tot = d_off + 2 * n_blocks;
@@ -324,32 +475,181 @@ extern "C" int gm_scan_create(const uint8_t *seq_ascii, int64_t n, const char *p
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(totals, d_tot, sizeof totals, cudaMemcpyDeviceToHost);
+    trace("scan: H2D + encode + count", t0);
     const int64_t nf = (int64_t)totals[0], nr = (int64_t)totals[1], nt = nf + nr;
     if (e == cudaSuccess && nt > 0) {
         e = dev_alloc((void **)&s->guides, (size_t)nt * 8, 0);
         if (e == cudaSuccess) e = dev_alloc((void **)&s->start, (size_t)nt * 4, 0);
         if (e == cudaSuccess) e = dev_alloc((void **)&s->pamcode, (size_t)nt * 2, 0);
+        if (e == cudaSuccess && session) e = dev_alloc((void **)&s->rec, (size_t)nt * 4, 0);
+        if (e == cudaSuccess && session) e = dev_alloc((void **)&s->strand, (size_t)nt, 0);
         if (e == cudaSuccess) {
-            scan_emit_kernel<<<(unsigned)n_blocks, SCAN_THREADS>>>(pp, n_words, lo, hi, va, off_f, off_r, (uint64_t)nf,
-                                                                   s->guides, s->start, s->pamcode);
-            count_launch();
+            if (session) {
+                uint64_t *F = d_FR, *R = d_FR + (n_rec + 1);
+                boundary_rank_kernel<<<(unsigned)(n_rec + 1), SCAN_THREADS>>>(pp, n_words, lo, hi, va, off_f, off_r, d_tot, s->rec_start, n_rec, F, R);
+                scan_emit_records_kernel<<<(unsigned)n_blocks, SCAN_THREADS>>>(pp, n_words, lo, hi, va, off_f, off_r, s->rec_start, n_rec, F, R,
+                                                                               s->guides, s->start, s->pamcode, s->rec, s->strand);
+                count_launch(2);
+            } else {
+                scan_emit_kernel<<<(unsigned)n_blocks, SCAN_THREADS>>>(pp, n_words, lo, hi, va, off_f, off_r, (uint64_t)nf,
+                                                                       s->guides, s->start, s->pamcode);
+                count_launch();
+            }
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
     }
+    if (session && e == cudaSuccess) { s->seq = d_seq; s->n_seq = n; d_seq = nullptr; }
     dev_free(d_seq, 0);
     dev_free(d_planes, 0);
     dev_free(d_blk, 0);
     dev_free(d_off, 0);
-    if (e != cudaSuccess) {
-        gm_scan_free(s);
-        *scan = nullptr;
-        return cuda_fail(e, "gm_scan_create", __FILE__, __LINE__);
-    }
+    dev_free(d_FR, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "gm_scan_create", __FILE__, __LINE__);
     s->n_fwd = nf;
     s->n_rev = nr;
-    *n_fwd = nf;
-    *n_rev = nr;
+    s->session = session;
+    s->n_rec = n_rec;
+    s->P = pp.P;
+    s->L = pp.L;
+    s->five_prime = pp.five_prime;
+    return GM_OK;
+}
+
+}  // namespace gm
+
+using namespace gm;
+
+extern "C" int gm_scan_free(void *scan) {
+    Scan *s = (Scan *)scan;
+    if (!s) return GM_OK;
+    dev_free(s->guides, 0);
+    dev_free(s->start, 0);
+    dev_free(s->pamcode, 0);
+    dev_free(s->rec, 0);
+    dev_free(s->strand, 0);
+    dev_free(s->seq, 0);
+    dev_free(s->rec_start, 0);
+    dev_free(s->first32, 0);
+    delete s;
+    return GM_OK;
+}
+
+static int scan_create_common(const uint8_t *seq_ascii, int64_t n, const int64_t *rec_start, int n_rec, const char *pam, int pam_len,
+                              int five_prime, int L, void **scan) {
+    GM_ARG(n >= 0 && (n == 0 || seq_ascii), "gm_scan_create: bad sequence buffer");
+    GM_ARG(pam && pam_len >= 1 && pam_len <= GM_MAX_PAM, "gm_scan_create: PAM length %d outside [1,%d]", pam_len, GM_MAX_PAM);
+    GM_ARG(L >= 1 && L <= GM_MAX_L, "gm_scan_create: L=%d outside [1,%d]", L, GM_MAX_L);
+    if (n > 0xFFFFFF00LL) { set_error("gm_scan_create: %lld bases exceed the uint32 coordinate range", (long long)n); return GM_ERR_RANGE; }
+    PamParams pp;
+    int rc = fill_params(pp, pam, pam_len, five_prime, L);
+    if (rc) return rc;
+    if (rec_start) {
+        GM_ARG(n_rec >= 1 && rec_start[0] == 0, "gm_session_create: record table must start at 0");
+        for (int r = 0; r < n_rec; r++) GM_ARG(rec_start[r + 1] > rec_start[r], "gm_session_create: record offsets must increase");
+        GM_ARG(rec_start[n_rec] == n + 1, "gm_session_create: last record offset must be n + 1 (records joined by one byte)");
+    }
+    Scan *s = new (std::nothrow) Scan();
+    if (!s) { set_error("out of host memory"); return GM_ERR_NOMEM; }
+    s->session = rec_start != nullptr;
+    s->P = pam_len; s->L = L; s->five_prime = five_prime ? 1 : 0; s->n_rec = n_rec;
+    *scan = s;
+    if (n == 0) return GM_OK;
+    rc = scan_build(s, seq_ascii, n, pp, rec_start, n_rec);
+    if (rc) { gm_scan_free(s); *scan = nullptr; }
+    return rc;
+}
+
+extern "C" int gm_scan_create(const uint8_t *seq_ascii, int64_t n, const char *pam, int pam_len, int five_prime, int L,
+                              void **scan, int64_t *n_fwd, int64_t *n_rev) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    GM_ARG(scan && n_fwd && n_rev, "gm_scan_create: NULL output pointer");
+    *scan = nullptr;
+    *n_fwd = *n_rev = 0;
+    rc = scan_create_common(seq_ascii, n, nullptr, 1, pam, pam_len, five_prime, L, scan);
+    if (rc) return rc;
+    *n_fwd = ((Scan *)*scan)->n_fwd;
+    *n_rev = ((Scan *)*scan)->n_rev;
+    return GM_OK;
+}
+
+extern "C" int gm_session_create(const uint8_t *seq_ascii, int64_t n, const int64_t *rec_start, int n_rec, const char *pam, int pam_len,
+                                 int five_prime, int L, void **session, int64_t *n_rows) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    GM_ARG(session && n_rows && rec_start, "gm_session_create: NULL pointer");
+    *session = nullptr;
+    *n_rows = 0;
+    rc = scan_create_common(seq_ascii, n, rec_start, n_rec, pam, pam_len, five_prime, L, session);
+    if (rc) return rc;
+    *n_rows = ((Scan *)*session)->n_fwd + ((Scan *)*session)->n_rev;
+    return GM_OK;
+}
+
+extern "C" int gm_session_free(void *session) { return gm_scan_free(session); }
+
+extern "C" int gm_scan_device_ptrs(void *scan, const uint64_t **d_guide2bit, const uint32_t **d_start, const uint16_t **d_pamcode, int64_t *n_rows) {
+    Scan *s = (Scan *)scan;
+    GM_ARG(s, "gm_scan_device_ptrs: NULL handle");
+    if (d_guide2bit) *d_guide2bit = s->guides;
+    if (d_start) *d_start = s->start;
+    if (d_pamcode) *d_pamcode = s->pamcode;
+    if (n_rows) *n_rows = s->n_fwd + s->n_rev;
+    return GM_OK;
+}
+
+extern "C" int gm_session_fetch_rows(void *session, uint64_t *guide2bit, uint32_t *start, uint16_t *pamcode, int32_t *rec, uint8_t *strand) {
+    Scan *s = (Scan *)session;
+    GM_ARG(s && s->session, "gm_session_fetch_rows: not a session handle");
+    const size_t nt = (size_t)(s->n_fwd + s->n_rev);
+    if (nt == 0) return GM_OK;
+    const double t0 = now_ms();
+    if (guide2bit) GM_CUDA(cudaMemcpyAsync(guide2bit, s->guides, nt * 8, cudaMemcpyDeviceToHost, 0));
+    if (start) GM_CUDA(cudaMemcpyAsync(start, s->start, nt * 4, cudaMemcpyDeviceToHost, 0));
+    if (pamcode) GM_CUDA(cudaMemcpyAsync(pamcode, s->pamcode, nt * 2, cudaMemcpyDeviceToHost, 0));
+    if (rec) GM_CUDA(cudaMemcpyAsync(rec, s->rec, nt * 4, cudaMemcpyDeviceToHost, 0));
+    if (strand) GM_CUDA(cudaMemcpyAsync(strand, s->strand, nt, cudaMemcpyDeviceToHost, 0));
+    GM_CUDA(cudaStreamSynchronize(0));
+    trace("session: fetch rows", t0);
+    return GM_OK;
+}
+
+extern "C" int gm_session_fetch_text(void *session, uint8_t *target_ascii, uint8_t *context, int width, uint8_t *edge) {
+    Scan *s = (Scan *)session;
+    GM_ARG(s && s->session, "gm_session_fetch_text: not a session handle");
+    GM_ARG(!context || (width >= 4 && width <= 1024), "gm_session_fetch_text: context width %d outside [4,1024]", width);
+    const int64_t nt = s->n_fwd + s->n_rev;
+    if (nt == 0) return GM_OK;
+    const double t0 = now_ms();
+    int rc = ensure_comp_table();
+    if (rc) return rc;
+    uint8_t *d_t = nullptr, *d_c = nullptr, *d_e = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (target_ascii) {
+        e = dev_alloc((void **)&d_t, (size_t)nt * s->L, 0);
+        if (e == cudaSuccess) {
+            decode_rows_kernel<<<(unsigned)((nt * s->L + 255) / 256), 256>>>(s->guides, nt, s->L, d_t);
+            count_launch();
+            e = cudaMemcpyAsync(target_ascii, d_t, (size_t)nt * s->L, cudaMemcpyDeviceToHost, 0);
+        }
+    }
+    if (e == cudaSuccess && context) {
+        e = dev_alloc((void **)&d_c, (size_t)nt * width, 0);
+        if (e == cudaSuccess && edge) e = dev_alloc((void **)&d_e, (size_t)nt, 0);
+        if (e == cudaSuccess) {
+            context_rows_kernel<<<(unsigned)((nt * width + 255) / 256), 256>>>(s->seq, s->rec_start, s->start, s->rec, s->strand, nt, s->P, s->L,
+                                                                               s->five_prime, width, d_c, d_e);
+            count_launch();
+            e = cudaMemcpyAsync(context, d_c, (size_t)nt * width, cudaMemcpyDeviceToHost, 0);
+            if (e == cudaSuccess && edge) e = cudaMemcpyAsync(edge, d_e, (size_t)nt, cudaMemcpyDeviceToHost, 0);
+        }
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    dev_free(d_t, 0); dev_free(d_c, 0); dev_free(d_e, 0);
+    trace("session: text columns", t0);
+    if (e != cudaSuccess) return cuda_fail(e, "gm_session_fetch_text", __FILE__, __LINE__);
     return GM_OK;
 }
 
@@ -359,8 +659,6 @@ extern "C" int gm_scan_create(const uint8_t *seq_ascii, int64_t n, const char *p
 // starting at win_start[i]; rows flagged in `revcomp` are reversed and complemented with Bio.Seq's IUPAC table
 // (other bytes unchanged).  A window that does not lie inside [0, n) is filled with '?' -- the host applies the
 // reference's literal Python slice semantics to those few rows near record ends.
-__constant__ uint8_t c_comp[256];
-
 __global__ void __launch_bounds__(256) gather_windows_kernel(const uint8_t *__restrict__ seq, int64_t n, const int64_t *__restrict__ win_start,
                                                              const uint8_t *__restrict__ revcomp, int64_t n_rows, int width,
                                                              uint8_t *__restrict__ out) {
@@ -381,15 +679,8 @@ extern "C" int gm_gather_windows(const uint8_t *seq_ascii, int64_t n, const int6
     GM_ARG(n >= 0 && n_rows >= 0 && width >= 1 && width <= 1024, "gm_gather_windows: bad size");
     if (n_rows == 0) return GM_OK;
     GM_ARG(win_start && revcomp && out && (n == 0 || seq_ascii), "gm_gather_windows: NULL buffer");
-    static bool table_set = false;
-    if (!table_set) {
-        uint8_t comp[256];
-        for (int c = 0; c < 256; c++) comp[c] = (uint8_t)c;
-        const char *from = "ACGTMRWSYKVHDBXNacgtmrwsykvhdbxn", *to = "TGCAKYWSRMBDHVXNtgcakywsrmbdhvxn";   // Bio.Seq complement
-        for (int k = 0; from[k]; k++) comp[(uint8_t)from[k]] = (uint8_t)to[k];
-        GM_CUDA(cudaMemcpyToSymbol(c_comp, comp, 256));
-        table_set = true;
-    }
+    rc = ensure_comp_table();
+    if (rc) return rc;
     uint8_t *d_seq = nullptr, *d_rc = nullptr, *d_out = nullptr;
     int64_t *d_ws = nullptr;
     cudaError_t e = dev_alloc((void **)&d_seq, (size_t)n + 16, 0);

@@ -7,7 +7,7 @@
 // j accepts the guide base at o + j", which is evaluated here for all offsets at once on the guide's bit planes:
 // for motif position j, pos_j = OR of the one-hot base masks of the accepted letters; match = AND_j (pos_j >> j),
 // restricted to offsets 0 .. L - len.  One thread per guide, 8 bytes in, 1 byte out: HBM bound.
-#include "common.cuh"
+#include "scan.cuh"
 
 namespace gm {
 
@@ -69,6 +69,11 @@ static int restriction_run(const uint64_t *d_guides, int64_t n, int L, const uin
     }
     GM_CUDA(cudaGetLastError());
     return GM_OK;
+}
+
+int restriction_dev(const uint64_t *d_guides, int64_t n, int L, const uint8_t *motif_sets, const int32_t *motif_len, int n_motifs,
+                    uint8_t *d_has_site, cudaStream_t st) {
+    return restriction_run(d_guides, n, L, motif_sets, motif_len, n_motifs, d_has_site, st);
 }
 
 }  // namespace gm

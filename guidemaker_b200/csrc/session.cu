@@ -1,0 +1,211 @@
+// session.cu -- the device-resident chain behind the four hot methods of guidemaker.core.
+//
+// A session (gm_session_create, pam_scan.cu) keeps the genome and the rows of the PAM scan in HBM.  The stages that the
+// reference runs one after the other on host strings
+//      find_unique_near_pam (core.py:388-416)  ->  create_index (core.py:418-467)  ->  get_neighbors (core.py:471-523)
+// take their input from that handle on one stream: nothing but the per-row results the host frame needs (1-byte flags,
+// the distinct-guide table, the (idx, dist) rows) crosses PCIe, and no stage re-uploads the guides.
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+
+#include "knn_common.cuh"
+#include "scan.cuh"
+
+namespace gm {
+
+__global__ void first_flag_kernel(const int32_t *__restrict__ first32, int64_t n, int32_t *__restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = first32[i] == (int32_t)i ? 1 : 0;
+}
+
+// uniq[rank[i]] = guides[i] for first occurrences; row2uniq[i] = rank[first32[i]]
+__global__ void uniq_scatter_kernel(const uint64_t *__restrict__ guides, const int32_t *__restrict__ first32, const int32_t *__restrict__ rank,
+                                    int64_t n, uint64_t *__restrict__ uniq, int32_t *__restrict__ row2uniq) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t f = first32[i];
+    const int32_t r = rank[f];
+    row2uniq[i] = r;
+    if (f == (int32_t)i) uniq[r] = guides[i];
+}
+
+static Scan *as_session(void *h) {
+    Scan *s = (Scan *)h;
+    return (s && s->session) ? s : nullptr;
+}
+
+}  // namespace gm
+
+using namespace gm;
+
+extern "C" int gm_session_info(void *session, int64_t *n_rows, int *n_rec, int *L, int *P, int *five_prime) {
+    Scan *s = as_session(session);
+    GM_ARG(s, "gm_session_info: not a session handle");
+    if (n_rows) *n_rows = s->n_fwd + s->n_rev;
+    if (n_rec) *n_rec = s->n_rec;
+    if (L) *L = s->L;
+    if (P) *P = s->P;
+    if (five_prime) *five_prime = s->five_prime;
+    return GM_OK;
+}
+
+extern "C" int gm_session_seed_dedup(void *session, int lsr, uint8_t *is_dup) {
+    Scan *s = as_session(session);
+    GM_ARG(s && is_dup, "gm_session_seed_dedup: bad argument");
+    const int64_t n = s->n_fwd + s->n_rev;
+    if (n == 0) return GM_OK;
+    const double t0 = now_ms();
+    uint8_t *d = nullptr;
+    GM_CUDA(dev_alloc((void **)&d, (size_t)n, 0));
+    int rc = dedup_dev(s->guides, n, s->L, lsr, s->five_prime, d, nullptr, nullptr, 0);
+    cudaError_t e = cudaSuccess;
+    if (rc == GM_OK) e = cudaMemcpyAsync(is_dup, d, (size_t)n, cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    dev_free(d, 0);
+    trace("session: seed flags", t0);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "gm_session_seed_dedup", __FILE__, __LINE__);
+    return GM_OK;
+}
+
+extern "C" int gm_session_restriction(void *session, const uint8_t *motif_sets, const int32_t *motif_len, int n_motifs, uint8_t *has_site) {
+    Scan *s = as_session(session);
+    GM_ARG(s && has_site, "gm_session_restriction: bad argument");
+    const int64_t n = s->n_fwd + s->n_rev;
+    if (n == 0) return GM_OK;
+    uint8_t *d = nullptr;
+    GM_CUDA(dev_alloc((void **)&d, (size_t)n, 0));
+    int rc = restriction_dev(s->guides, n, s->L, motif_sets, motif_len, n_motifs, d, 0);
+    cudaError_t e = cudaSuccess;
+    if (rc == GM_OK) e = cudaMemcpyAsync(has_site, d, (size_t)n, cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    dev_free(d, 0);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "gm_session_restriction", __FILE__, __LINE__);
+    return GM_OK;
+}
+
+// Distinct guides in first-occurrence order (the deterministic stand-in for list(set(targets)), core.py:446) -> index.
+extern "C" int gm_session_index(void *session, int metric, void **index, uint64_t *uniq2bit, int32_t *row2uniq, int64_t *n_u) {
+    Scan *s = as_session(session);
+    GM_ARG(s && index && n_u, "gm_session_index: bad argument");
+    *index = nullptr;
+    *n_u = 0;
+    const int64_t n = s->n_fwd + s->n_rev;
+    GM_ARG(n >= 1, "gm_session_index: empty guide table");
+    const double t0 = now_ms();
+    cudaStream_t st = 0;
+    int32_t *d_flag = nullptr, *d_rank = nullptr, *d_r2u = nullptr;
+    uint64_t *d_uniq = nullptr;
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int rc = GM_OK;
+    cudaError_t e = cudaSuccess;
+    if (!s->first32) e = dev_alloc((void **)&s->first32, (size_t)n * 4, st);
+    if (e == cudaSuccess) rc = dedup_dev(s->guides, n, GM_MAX_L, 0, 0, nullptr, nullptr, s->first32, st);
+    if (rc == GM_OK && e == cudaSuccess) e = dev_alloc((void **)&d_flag, (size_t)(n + 1) * 4, st);
+    if (rc == GM_OK && e == cudaSuccess) e = dev_alloc((void **)&d_rank, (size_t)(n + 1) * 4, st);
+    if (rc == GM_OK && e == cudaSuccess) e = dev_alloc((void **)&d_r2u, (size_t)n * 4, st);
+    if (rc == GM_OK && e == cudaSuccess) e = dev_alloc((void **)&d_uniq, (size_t)n * 8, st);
+    int32_t last[2] = {0, 0};
+    if (rc == GM_OK && e == cudaSuccess) {
+        const unsigned grid = (unsigned)((n + 255) / 256);
+        first_flag_kernel<<<grid, 256, 0, st>>>(s->first32, n, d_flag);
+        e = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_flag, d_rank, (int)n, st);
+        if (e == cudaSuccess) e = dev_alloc(&d_tmp, tmp_bytes, st);
+        if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_flag, d_rank, (int)n, st);
+        if (e == cudaSuccess) {
+            uniq_scatter_kernel<<<grid, 256, 0, st>>>(s->guides, s->first32, d_rank, n, d_uniq, d_r2u);
+            count_launch(4);
+            e = cudaMemcpyAsync(&last[0], d_rank + (n - 1), 4, cudaMemcpyDeviceToHost, st);
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&last[1], d_flag + (n - 1), 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    const int64_t nu = (int64_t)last[0] + last[1];
+    if (rc == GM_OK && e == cudaSuccess) {
+        rc = gm_index_create_dev(d_uniq, nu, s->L, metric, index, st);
+        if (rc == GM_OK && uniq2bit) e = cudaMemcpyAsync(uniq2bit, d_uniq, (size_t)nu * 8, cudaMemcpyDeviceToHost, st);
+        if (rc == GM_OK && e == cudaSuccess && row2uniq) e = cudaMemcpyAsync(row2uniq, d_r2u, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    dev_free(d_flag, st); dev_free(d_rank, st); dev_free(d_r2u, st); dev_free(d_uniq, st); dev_free(d_tmp, st);
+    trace("session: distinct guides + index", t0);
+    if (rc == GM_OK && e != cudaSuccess) {
+        if (*index) { gm_index_free(*index); *index = nullptr; }
+        return cuda_fail(e, "gm_session_index", __FILE__, __LINE__);
+    }
+    if (rc) return rc;
+    *n_u = nu;
+    return GM_OK;
+}
+
+// kNN of the rows selected by `qmask` (one byte per row, host; the query mask of core.py:495), in row order.
+// out_* receive n_q rows (n_q = number of non-zero mask bytes, checked).  With `device_out` the outputs are DEVICE
+// pointers and the call returns without synchronising `stream` (multi-GPU: the caller all-gathers them first).
+static int session_knn(void *session, void *index, const uint8_t *qmask, int64_t n_q, int k, int32_t *out_idx, uint8_t *out_dist,
+                       bool device_out, cudaStream_t st) {
+    Scan *s = as_session(session);
+    GM_ARG(s && index && qmask, "gm_session_knn: bad argument");
+    GM_ARG(k >= 1 && k <= GM_MAX_K, "gm_session_knn: k=%d outside [1,%d]", k, GM_MAX_K);
+    const int64_t n = s->n_fwd + s->n_rev;
+    if (n == 0 || n_q == 0) return GM_OK;
+    GM_ARG(out_idx && out_dist && n_q > 0 && n_q <= n, "gm_session_knn: bad output buffers / n_q");
+    const double t0 = now_ms();
+    uint8_t *d_mask = nullptr;
+    uint64_t *d_q = nullptr;
+    int64_t *d_cnt = nullptr;
+    int32_t *d_idx = device_out ? out_idx : nullptr;
+    uint8_t *d_dist = device_out ? out_dist : nullptr;
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int64_t cnt = -1;
+    int rc = GM_OK;
+    cudaError_t e = dev_alloc((void **)&d_mask, (size_t)n, st);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_q, (size_t)n_q * 8 + 8, st);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_cnt, 8, st);
+    if (e == cudaSuccess && !device_out) e = dev_alloc((void **)&d_idx, (size_t)n_q * k * 4, st);
+    if (e == cudaSuccess && !device_out) e = dev_alloc((void **)&d_dist, (size_t)n_q * k, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_mask, qmask, (size_t)n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        if (n_q == n) {                                            // every row is a query: no compaction (mask checked below)
+            e = cudaMemcpyAsync(d_q, s->guides, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
+            cnt = n;
+        } else {
+            // the mask must select exactly n_q rows or the compaction would overrun d_q: count first
+            e = cub::DeviceSelect::Flagged(nullptr, tmp_bytes, s->guides, d_mask, d_q, d_cnt, (int)n, st);
+            if (e == cudaSuccess) e = dev_alloc(&d_tmp, tmp_bytes, st);
+            int64_t host_cnt = 0;
+            for (int64_t i = 0; i < n; i++) host_cnt += qmask[i] != 0;
+            if (host_cnt != n_q) { rc = GM_ERR_ARG; set_error("gm_session_knn: qmask selects %lld rows, n_q = %lld", (long long)host_cnt, (long long)n_q); }
+            if (rc == GM_OK && e == cudaSuccess) e = cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, s->guides, d_mask, d_q, d_cnt, (int)n, st);
+            count_launch(2);
+            cnt = n_q;
+        }
+    }
+    if (rc == GM_OK && e == cudaSuccess) rc = gm_knn_dev(index, d_q, cnt, k, d_idx, d_dist, st);
+    if (rc == GM_OK && e == cudaSuccess && !device_out) {
+        e = cudaMemcpyAsync(out_idx, d_idx, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_dist, d_dist, (size_t)n_q * k, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    dev_free(d_mask, st); dev_free(d_q, st); dev_free(d_cnt, st); dev_free(d_tmp, st);
+    if (!device_out) { dev_free(d_idx, st); dev_free(d_dist, st); }
+    trace("session: kNN", t0);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "gm_session_knn", __FILE__, __LINE__);
+    return GM_OK;
+}
+
+extern "C" int gm_session_knn(void *session, void *index, const uint8_t *qmask, int64_t n_q, int k, int32_t *out_idx, uint8_t *out_dist) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    return session_knn(session, index, qmask, n_q, k, out_idx, out_dist, false, 0);
+}
+
+extern "C" int gm_session_knn_dev(void *session, void *index, const uint8_t *qmask, int64_t n_q, int k, int32_t *d_out_idx,
+                                  uint8_t *d_out_dist, void *stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    return session_knn(session, index, qmask, n_q, k, d_out_idx, d_out_dist, true, (cudaStream_t)stream);
+}

@@ -54,6 +54,20 @@ def _gather_rows(local: np.ndarray, n_total: int, rank: int, world_size: int) ->
     return np.concatenate(parts, axis=0)
 
 
+def broadcast_rank0(a: np.ndarray) -> np.ndarray:
+    """rank 0's array on every rank (same shape and dtype everywhere); identity for a single process."""
+    rank, ws = world()
+    if ws == 1:
+        return a
+    import torch
+    import torch.distributed as dist
+    device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    raw = np.ascontiguousarray(a).view(np.uint8).copy()
+    t = torch.from_numpy(raw).to(device)
+    dist.broadcast(t, src=0)
+    return t.cpu().numpy().view(a.dtype).reshape(a.shape)
+
+
 def sharded_knn(index, q2bit: np.ndarray, k: int):
     """kNN of all queries with the rows split over the ranks; every rank returns the full result."""
     rank, ws = world()
@@ -62,6 +76,62 @@ def sharded_knn(index, q2bit: np.ndarray, k: int):
     lo, hi = shard_bounds(len(q2bit), rank, ws)
     idx, dist_ = index.knn_packed(q2bit[lo:hi], k)
     return _gather_rows(idx, len(q2bit), rank, ws), _gather_rows(dist_, len(q2bit), rank, ws)
+
+
+_pinned = {}
+
+
+def _pinned_like(name: str, shape, dtype):
+    """page-locked host staging buffers, kept between calls (allocating them costs more than the copy)"""
+    import torch
+    key = (name, tuple(shape), dtype)
+    buf = _pinned.get(name)
+    if buf is None or buf[0] != key:
+        buf = (key, torch.empty(tuple(shape), dtype=dtype, pin_memory=True))
+        _pinned[name] = buf
+    return buf[1]
+
+
+def sharded_session_knn(sess, engine, qmask: np.ndarray, k: int):
+    """kNN of the masked rows of a device-resident scan (``_capi.Session``) with the query rows split over the ranks.
+
+    Single process: one call, results straight into host arrays.  NCCL: every rank compacts and searches ITS slice of
+    the query rows on the device, the fixed-size result rows are all-gathered device-to-device, and only then copied
+    once into page-locked host memory -- nothing bounces through the host between the kernel and the collective."""
+    rank, ws = world()
+    if ws == 1:
+        return sess.knn(engine, qmask, k)
+    import torch
+    import torch.distributed as dist
+    qrows = np.flatnonzero(qmask)
+    nq = len(qrows)
+    lo, hi = shard_bounds(nq, rank, ws)
+    local = np.zeros(len(qmask), np.uint8)
+    local[qrows[lo:hi]] = 1
+    if dist.get_backend() != "nccl":                          # CPU test plumbing (gloo): host arrays through _gather_rows
+        idx, dist_ = sess.knn(engine, local, k)
+        return _gather_rows(idx, nq, rank, ws), _gather_rows(dist_, nq, rank, ws)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rows = max(shard_bounds(nq, r, ws)[1] - shard_bounds(nq, r, ws)[0] for r in range(ws))
+    d_idx = torch.full((rows, k), -1, dtype=torch.int32, device=dev)
+    d_dist = torch.full((rows, k), 255, dtype=torch.uint8, device=dev)
+    g_idx = torch.empty((ws * rows, k), dtype=torch.int32, device=dev)
+    g_dist = torch.empty((ws * rows, k), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    sess.knn_dev(engine, local, k, d_idx.data_ptr(), d_dist.data_ptr(), stream)
+    dist.all_gather_into_tensor(g_idx, d_idx)
+    dist.all_gather_into_tensor(g_dist, d_dist)
+    h_idx = _pinned_like("idx", g_idx.shape, torch.int32)
+    h_dist = _pinned_like("dist", g_dist.shape, torch.uint8)
+    h_idx.copy_(g_idx, non_blocking=True)
+    h_dist.copy_(g_dist, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    out_i, out_d = h_idx.numpy().reshape(ws, rows, k), h_dist.numpy().reshape(ws, rows, k)
+    if nq == ws * rows:
+        return out_i.reshape(nq, k).copy(), out_d.reshape(nq, k).copy()
+    sizes = [shard_bounds(nq, r, ws)[1] - shard_bounds(nq, r, ws)[0] for r in range(ws)]
+    return (np.concatenate([out_i[r, : sizes[r]] for r in range(ws)], axis=0),
+            np.concatenate([out_d[r, : sizes[r]] for r in range(ws)], axis=0))
 
 
 def sharded_min_dist(index, q2bit: np.ndarray) -> np.ndarray:

@@ -30,6 +30,12 @@
  *     Neighbours are ordered ascending by (distance, target index); rows with fewer than k
  *     targets are padded with idx = -1, dist = 255.
  *   - There is no CPU fallback: without a CUDA device of compute capability 10.x gm_init fails.
+ *   - Threads and streams: a handle (scan, session, index) must be used by ONE thread and ONE stream at a time -- an
+ *     index owns a scratch buffer that every query call on it reuses, so two concurrent gm_knn* calls on the same index
+ *     (from two threads, or enqueued on two streams without an event between them) race.  Different handles are
+ *     independent.  The profiling counters (gm_prof_*) and the tuning defaults (gm_knn_tune / gm_knn_engine) are
+ *     process-wide and unsynchronised: set them before starting worker threads.
+ *     gm_session_create / gm_scan_create / the host-pointer calls use the default stream.
  */
 #ifndef GM_B200_H
 #define GM_B200_H
@@ -88,6 +94,41 @@ int gm_seed_dedup(const uint64_t *guide2bit, int64_t n, int L, int lsr, int five
 /* first_row[i] = smallest row whose key equals keys[i] (distinct guides in first-occurrence
  * order are the rows with first_row[i] == i). n < 2^31. */
 int gm_first_occurrence(const uint64_t *keys, int64_t n, int64_t *first_row);
+
+/* device-resident variants: pointers into HBM, enqueued on `stream`, no synchronisation.  d_first_row is int32 (rows < 2^31). */
+int gm_seed_dedup_dev(const uint64_t *d_guide2bit, int64_t n, int L, int lsr, int five_prime, uint8_t *d_is_dup, void *stream);
+int gm_first_occurrence_dev(const uint64_t *d_keys, int64_t n, int32_t *d_first_row, void *stream);
+/* the rows of a finished scan, still in HBM (valid until gm_scan_free): feed them to the *_dev entry points */
+int gm_scan_device_ptrs(void *scan, const uint64_t **d_guide2bit, const uint32_t **d_start, const uint16_t **d_pamcode, int64_t *n_rows);
+
+/* ---- session: the four hot methods chained on the device ------------------------------------------------------------
+ * A session is a scan that (a) takes a multi-record genome -- records joined by ONE invalid byte, rec_start[r] = offset
+ * of record r in seq_ascii, rec_start[n_rec] = n + 1 -- and emits the rows in the reference's order (per record: forward
+ * hits ascending, then reverse hits ascending; core.py:254-284) with record-relative coordinates, and (b) keeps genome and
+ * rows resident in HBM so that the later stages run off the handle without re-uploading anything:
+ *   gm_session_fetch_rows   the numeric columns of find_targets' frame (any pointer may be NULL)
+ *   gm_session_fetch_text   `target` as ASCII (n_rows x L) and the 30-nt context `target_seq30` (n_rows x width) gathered
+ *                           from the resident genome (core.py:156,184,210-211,237); edge[i] = 1 where the window leaves
+ *                           the record (filled with '?': the caller applies Python's slice semantics to those rows)
+ *   gm_session_seed_dedup   find_unique_near_pam's keep-first flags (core.py:402-416)
+ *   gm_session_restriction  check_restriction_enzymes' flags (core.py:354-377), motifs as for gm_restriction_scan
+ *   gm_session_index        distinct guides in first-occurrence order -> kNN index (core.py:446-467); uniq2bit must have
+ *                           room for n_rows entries (n_u are written), row2uniq[i] = position of row i's guide in it
+ *   gm_session_knn          get_neighbors (core.py:495-503): kNN of the rows with qmask[i] != 0 (host bytes), in row order;
+ *                           n_q must equal the number of selected rows.  _dev: outputs are device pointers, no sync.
+ * All calls on one session / index handle must come from one thread at a time. */
+int gm_session_create(const uint8_t *seq_ascii, int64_t n, const int64_t *rec_start, int n_rec, const char *pam, int pam_len,
+                      int five_prime, int L, void **session, int64_t *n_rows);
+int gm_session_info(void *session, int64_t *n_rows, int *n_rec, int *L, int *P, int *five_prime);
+int gm_session_fetch_rows(void *session, uint64_t *guide2bit, uint32_t *start, uint16_t *pamcode, int32_t *rec, uint8_t *strand);
+int gm_session_fetch_text(void *session, uint8_t *target_ascii, uint8_t *context, int width, uint8_t *edge);
+int gm_session_seed_dedup(void *session, int lsr, uint8_t *is_dup);
+int gm_session_restriction(void *session, const uint8_t *motif_sets, const int32_t *motif_len, int n_motifs, uint8_t *has_site);
+int gm_session_index(void *session, int metric, void **index, uint64_t *uniq2bit, int32_t *row2uniq, int64_t *n_u);
+int gm_session_knn(void *session, void *index, const uint8_t *qmask, int64_t n_q, int k, int32_t *out_idx, uint8_t *out_dist);
+int gm_session_knn_dev(void *session, void *index, const uint8_t *qmask, int64_t n_q, int k, int32_t *d_out_idx,
+                       uint8_t *d_out_dist, void *stream);
+int gm_session_free(void *session);
 
 /* ---- K6: restriction-site flag ------------------------------------------------------------------
  * has_site[i] = 1 iff some motif occurs in guide i at any offset.  A motif is a string of letter sets:

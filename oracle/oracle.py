@@ -68,6 +68,10 @@ def lib() -> ctypes.CDLL:
                                    ctypes.c_void_p, ctypes.c_int]
         L.gmo_restriction.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int,
                                       ctypes.c_void_p]
+        L.gmo_knn_hamming_fast.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.gmo_knn_hamming_fast.restype = ctypes.c_int
+        L.gmo_has_avx512_popcnt.restype = ctypes.c_int
         for f in (L.gmo_pam_scan, L.gmo_seed_dedup, L.gmo_first_occurrence, L.gmo_knn, L.gmo_min_dist, L.gmo_num_threads,
                   L.gmo_restriction):
             f.restype = ctypes.c_int
@@ -156,6 +160,23 @@ def c_knn(targets, queries, L: int, metric: int, k: int, threads: int = 0):
     if rc != 0:
         raise RuntimeError(rc)
     return idx, dist
+
+
+def c_knn_hamming_fast(targets, queries, L: int, k: int, threads: int = 0):
+    """gmo_knn(metric 0) with a tuned schedule (AVX-512 VPOPCNTD when available, query blocking): the CPU arm of bench.py.
+    Identical output; gmo_knn remains the checker."""
+    t = np.ascontiguousarray(targets, np.uint64)
+    q = np.ascontiguousarray(queries, np.uint64)
+    idx = np.empty((len(q), k), np.int32)
+    dist = np.empty((len(q), k), np.uint8)
+    rc = lib().gmo_knn_hamming_fast(_ptr(t), len(t), _ptr(q), len(q), L, k, _ptr(idx), _ptr(dist), threads)
+    if rc:
+        raise RuntimeError("gmo_knn_hamming_fast failed: %d" % rc)
+    return idx, dist
+
+
+def has_avx512_popcnt() -> bool:
+    return bool(lib().gmo_has_avx512_popcnt())
 
 
 def c_min_dist(targets, queries, L: int, metric: int, threads: int = 0):

@@ -260,3 +260,33 @@ def case_errors(config_yaml):
         guidemaker.core.TargetProcessor(targets=t, lsr=10).find_unique_near_pam()
     assert guidemaker.core.extend_ambiguous_dna('NGG') == ['GGG', 'AGG', 'TGG', 'CGG']                # test_core.py:254-257
     assert np.array_equal(encode_guides(["ACGT"]), np.array([0b11100100], np.uint64))
+
+
+def case_unsorted_contigs(config_yaml):
+    """Contig ids that are NOT in sorted order (chr2, chr10, chr1): the reference's per-record concat leaves `seqid` as
+    plain strings, so export_bed (core.py:525-543) sorts the contigs lexicographically -- chr1, chr10, chr2 -- and rows
+    within a contig by start.  The frame itself stays in record order."""
+    rng = np.random.default_rng(3)
+    recs = [Rec(name, "".join(rng.choice(list("ACGT"), size=4000))) for name in ("chr2", "chr10", "chr1")]
+    df = guidemaker.PamTarget("NGG", "3prime", "hamming").find_targets(recs, 20)
+    assert list(dict.fromkeys(df["seqid"].astype(str))) == ["chr2", "chr10", "chr1"]          # frame: record order
+    # every row's coordinates are record-relative and the guide is what the record holds there
+    for i in (0, len(df) // 2, len(df) - 1):
+        row = df.iloc[i]
+        seq = {r.id: r.seq for r in recs}[str(row["seqid"])]
+        piece = seq[int(row["start"]): int(row["stop"])]
+        assert row["target"] == (piece if row["strand"] else guidemaker.core._reverse_complement(piece))
+    tp = guidemaker.TargetProcessor(df, lsr=10, editdist=2, knum=2)
+    tp.find_unique_near_pam()
+    bed = tp.export_bed()
+    chroms = bed["chrom"].astype(str).tolist()
+    assert list(dict.fromkeys(chroms)) == ["chr1", "chr10", "chr2"]                           # lexicographic, as the reference
+    assert chroms == sorted(chroms)
+    for c in ("chr1", "chr10", "chr2"):
+        st = bed.loc[bed["chrom"].astype(str) == c, "chromstart"].to_numpy()
+        assert (np.diff(st.astype(np.int64)) >= 0).all()
+    # the literal reference recipe on the same rows (plain-string chrom column) gives the same order
+    ref = tp.targets.loc[tp.targets["isseedduplicated"] == False, ["seqid", "start", "stop", "target", "strand"]].copy()  # noqa: E712
+    ref["seqid"] = ref["seqid"].astype(str)
+    ref = ref.sort_values(by=["seqid", "start"])
+    assert ref["target"].tolist() == bed["name"].tolist()

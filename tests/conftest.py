@@ -91,6 +91,59 @@ class _OracleIndex:
         pass
 
 
+class _OracleSession:
+    """Checker stand-in for guidemaker_b200._capi.Session (tests only): the same row order, coordinates, text columns
+    and chained stages, restated with the CPU oracle's primitives and plain numpy."""
+
+    def __init__(self, buf, rec_start, pam, five_prime, L):
+        from oracle import oracle as O
+        if any(c not in O.IUPAC for c in pam) or not (1 <= L <= 27):
+            raise ValueError("bad PAM / L")
+        self._O, self.L, self.P, self.five_prime = O, int(L), len(pam), bool(five_prime)
+        self.buf = np.ascontiguousarray(np.frombuffer(buf, np.uint8) if not isinstance(buf, np.ndarray) else buf)
+        self.rec_start = np.asarray(rec_start, np.int64)
+        g, gstart, p, nf, nr = O.c_pam_scan(self.buf.tobytes(), pam, five_prime, L)
+        strand = np.zeros(nf + nr, dtype=bool)
+        strand[:nf] = True
+        rec = np.searchsorted(self.rec_start, gstart.astype(np.int64), side="right") - 1
+        order = np.argsort(rec, kind="stable")               # per record: forward block, then reverse block
+        self.g, self.p, self.strand, self.rec = g[order], p[order], strand[order], rec[order].astype(np.int32)
+        self.gstart = gstart[order].astype(np.int64)
+        self.start = (self.gstart - self.rec_start[self.rec]).astype(np.uint32)
+        self.n_rows = len(self.g)
+
+    def fetch_rows(self):
+        return self.g, self.start, self.p, self.rec, self.strand
+
+    def fetch_text(self, width=30):
+        from guidemaker_b200._encode import decode_matrix
+        st, L, P, five = self.start.astype(np.int64), self.L, self.P, self.five_prime
+        ms = np.where(self.strand, st - P, st + L) if five else np.where(self.strand, st + L, st - P)
+        a = np.where(self.strand == five, ms - 3, ms + P - (width - 3))
+        lens = (self.rec_start[1:] - self.rec_start[:-1] - 1)[self.rec]
+        interior = (a >= 0) & (a + width <= lens)
+        ctx = self._O.np_gather_windows(self.buf, np.where(interior, a + self.rec_start[self.rec], -1), ~self.strand, width)
+        return decode_matrix(self.g, L), ctx, ~interior
+
+    def seed_dedup(self, lsr):
+        return self._O.c_seed_dedup(self.g, self.L, lsr, self.five_prime)
+
+    def restriction(self, motifs):
+        return self._O.c_restriction(self.g, self.L, list(motifs))
+
+    def build_index(self, metric):
+        first = self._O.c_first_occurrence(self.g)
+        is_first = first == np.arange(len(self.g))
+        uniq = np.ascontiguousarray(self.g[is_first])
+        return _OracleIndex(uniq, self.L, metric), uniq, ((np.cumsum(is_first) - 1)[first]).astype(np.int32)
+
+    def knn(self, index, qmask, k):
+        return index.knn(np.ascontiguousarray(self.g[np.asarray(qmask).astype(bool)]), k)
+
+    def close(self):
+        pass
+
+
 @pytest.fixture
 def oracle_engine(monkeypatch):
     """Route the product's C-ABI calls to the CPU oracle so the HOST logic (frame assembly, masks,
@@ -109,8 +162,24 @@ def oracle_engine(monkeypatch):
     monkeypatch.setattr(_capi, "gather_windows", lambda seq, ws, rc, w: O.np_gather_windows(seq, ws, rc, w))
     monkeypatch.setattr(_capi, "restriction_scan", lambda g, L, motifs: O.c_restriction(g, L, motifs))
     monkeypatch.setattr(_capi, "Index", _OracleIndex)
+    monkeypatch.setattr(_capi, "Session", _OracleSession)
     monkeypatch.setattr(_capi, "init", lambda device=None: None)
     return "oracle"
+
+
+def _gpu_visible() -> bool:
+    return os.path.exists("/dev/nvidiactl") or os.path.exists("/dev/nvidia0")
+
+
+def pytest_collection_modifyitems(config, items):
+    """On a box without a GPU the `gpu` tests are skipped (not errors); on a GPU box nothing is skipped, so a missing or
+    unloadable libgm_b200.so still fails loudly there."""
+    if _gpu_visible():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device on this box (gpu tests run on the B200 box: pytest -m gpu)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
 
 
 @pytest.fixture

@@ -38,3 +38,7 @@ def test_controls(oracle_engine, controls_ref, carsonella, synthetic_ref, config
 
 def test_errors(oracle_engine, config_yaml):
     C.case_errors(config_yaml)
+
+
+def test_unsorted_contigs(oracle_engine, config_yaml):
+    C.case_unsorted_contigs(config_yaml)

@@ -40,3 +40,8 @@ def test_controls(cuda_engine, controls_ref, carsonella, synthetic_ref, config_y
 
 def test_errors(cuda_engine, config_yaml):
     C.case_errors(config_yaml)
+
+
+@pytest.mark.gpu
+def test_unsorted_contigs(cuda_engine, config_yaml):
+    C.case_unsorted_contigs(config_yaml)

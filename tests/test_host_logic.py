@@ -190,3 +190,58 @@ def test_sharded_knn_gloo(world_size, tmp_path):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and "RANK_OK %d" % r in o, o
+
+
+_API_WORKER = r'''
+import sys
+sys.path.insert(0, %(root)r)
+import numpy as np, yaml, tempfile
+import torch.distributed as dist
+from unittest import mock
+from guidemaker_b200 import _capi, core
+from tests.conftest import _OracleIndex, _OracleSession, Rec
+rank, ws = int(sys.argv[1]), int(sys.argv[2])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=ws)
+_capi.Index, _capi.Session, _capi.init = _OracleIndex, _OracleSession, (lambda device=None: None)
+rng = np.random.default_rng(11)
+recs = [Rec("c%%d" %% i, "".join(rng.choice(list("ACGT"), size=6000))) for i in range(3)]
+cfg = tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False)
+yaml.safe_dump({"NMSLIB": {"M": 16, "efc": 10, "post": 1, "ef": 9}, "CONTROL": {"MINIMUM_HMDIST": 3, "CONTROL_SEARCH_MULTIPLE": [10, 100]}}, cfg)
+cfg.close()
+df = core.PamTarget("NGG", "3prime", "hamming").find_targets(recs, 20)
+tp = core.TargetProcessor(df, lsr=10, editdist=2, knum=3)
+tp.find_unique_near_pam(); tp.create_index(cfg.name); tp.get_neighbors(cfg.name)
+# every rank must hold the same, complete neighbour table
+g, _, _, _, _ = _OracleSession(b"N".join(r.seq.encode() for r in recs), np.cumsum([0] + [len(r) + 1 for r in recs]), "NGG", False, 20).fetch_rows()
+from oracle import oracle as O
+uniq, _ = O.unique_first_order(g)
+qmask = ~tp.targets["isseedduplicated"].to_numpy()
+oi, od = O.c_knn(uniq, g[qmask], 20, 0, 3)
+keep = od[:, 1] >= 2
+assert len(tp.neighbors) == len(set(g[qmask][keep].tolist())), (len(tp.neighbors), int(keep.sum()))
+# controls: DIFFERENT numpy seeds per rank -- rank 0's draw must be the one every rank searches and returns
+np.random.seed(100 + rank)
+cmin, cmed, cdf = tp.get_control_seqs(recs, configpath=cfg.name, length=20, n=20)
+seqs = cdf["Sequences"].tolist()
+gathered = [None] * ws
+dist.all_gather_object(gathered, (seqs, cdf["Hamming distance"].tolist()))
+assert all(x == gathered[0] for x in gathered), "ranks returned different control tables"
+from guidemaker_b200._encode import encode_guides
+true = O.c_min_dist(uniq, encode_guides(seqs, 20), 20, 0)
+assert [float(x) for x in true] == cdf["Hamming distance"].tolist(), "control distances do not belong to the returned sequences"
+dist.barrier(); dist.destroy_process_group()
+print("RANK_OK", rank)
+'''
+
+
+def test_api_under_two_ranks_gloo(tmp_path):
+    """find_targets -> get_neighbors -> get_control_seqs under a 2-rank group whose ranks seed numpy differently:
+    the query rows are sharded, every rank ends with the full result, and the controls are rank 0's draw."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "api_worker.py"
+    script.write_text(_API_WORKER % {"root": ROOT, "port": port})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), "2"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and "RANK_OK %d" % r in o, o

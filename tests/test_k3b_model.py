@@ -106,3 +106,79 @@ def test_out_of_order_tiles_can_lose_ties():
         lists = run_protocol(dist, 3, tile=32, rng=rng, in_order=False, max_lag=1)
         bad += sum(lists[q] != brute_topk(dist[q], 3) for q in range(dist.shape[0]))
     assert bad > 0
+
+
+# ---- the K encoding of knn_tc.cu: 3 bytes per position, ternary query side, bias word last -----------------------------
+def _permute_bits(x):
+    r = 0
+    for p in range(32):
+        r |= ((x >> p) & 1) << ((p >> 2) + 8 * (p & 3))
+    return r
+
+
+def _k_chunks(L):
+    words = 3 * ((L + 3) // 4) + 1
+    return (((words + 3) // 4) + 1) & ~1
+
+
+def _planes(codes):
+    lo = sum((int(c) & 1) << i for i, c in enumerate(codes))
+    hi = sum((int(c) >> 1) << i for i, c in enumerate(codes))
+    return _permute_bits(lo), _permute_bits(hi)
+
+
+def _bytes_of(word):
+    return [(word >> (8 * m)) & 0xFF for m in range(4)]
+
+
+def _target_row(codes, L):
+    """B operand row of one target: int8 values, as the producer warps write them"""
+    lo, hi = _planes(codes)
+    e = [lo & ~hi, hi & ~lo, lo & hi]
+    kw = 4 * _k_chunks(L)
+    row = []
+    for w in range(kw):
+        word = (1 | (64 << 8)) if w == kw - 1 else (e[w % 3] >> (w // 3)) & 0x01010101
+        row += _bytes_of(word)
+    return np.array(row, dtype=np.uint8).view(np.int8).astype(np.int64)
+
+
+def _query_row(c1, c2, tau1, tau2, L):
+    """A operand row of two queries (weights 1 and 64) with their bias bytes"""
+    lmask = _permute_bits((1 << L) - 1)
+    kw = 4 * _k_chunks(L)
+    pl = [_planes(c1), _planes(c2)]
+    eA = [~(lo | hi) & lmask for lo, hi in pl]
+    e = [[lo & ~hi, hi & ~lo, lo & hi] for lo, hi in pl]
+    row = []
+    for w in range(kw):
+        if w == kw - 1:
+            b = [31 - L + t + bin(a).count("1") for t, a in zip((tau1, tau2), eA)]
+            row += [b[0], b[1], 0, 0]
+        else:
+            x = [(e[s][w % 3] >> (w // 3)) & 0x01010101 for s in range(2)]
+            a = [(eA[s] >> (w // 3)) & 0x01010101 for s in range(2)]
+            pos, neg = _bytes_of(x[0] + (x[1] << 6)), _bytes_of(a[0] + (a[1] << 6))
+            row += [(p - n) & 0xFF for p, n in zip(pos, neg)]                  # __vsub4
+    return np.array(row, dtype=np.uint8).view(np.int8).astype(np.int64)
+
+
+@pytest.mark.parametrize("L", [1, 4, 5, 8, 9, 12, 16, 17, 20, 21, 23, 24, 25, 27])
+def test_k_encoding_counts_matches_and_flags(L):
+    rng = np.random.default_rng(L)
+    assert _k_chunks(L) == (2 if L <= 8 else 4 if L <= 20 else 6)
+    for _ in range(40):
+        q1, q2, t = (rng.integers(0, 4, size=L) for _ in range(3))
+        if rng.random() < 0.3:
+            q1 = np.zeros(L, dtype=np.int64)                                   # all-A query: the most negative data bytes
+        if rng.random() < 0.3:
+            t = q2.copy()
+        tau1, tau2 = int(rng.integers(0, 32)), int(rng.integers(0, 32))
+        A, B = _query_row(q1, q2, tau1, tau2, L), _target_row(t, L)
+        assert np.abs(A).max() <= 127 and len(A) == 16 * _k_chunks(L)
+        acc = int(A @ B)
+        m1, m2 = int((q1 == t).sum()), int((q2 == t).sum())
+        assert acc == (m1 + 31 - L + tau1) + 64 * (m2 + 31 - L + tau2)
+        assert 0 <= acc <= 4030                                                 # fits the packed 16-bit TMEM read-out
+        assert bool(acc & (1 << 5)) == ((L - m1) < tau1)                        # flag iff strictly closer than the bound
+        assert bool(acc & (1 << 11)) == ((L - m2) < tau2)

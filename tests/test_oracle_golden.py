@@ -231,3 +231,14 @@ def test_restriction_c_equals_literal_restatement():
             for r in set(enz):
                 motifs += [r.upper(), O.reverse_complement(r.upper())]
             assert np.array_equal(O.c_restriction(g, L, motifs), O.py_restriction(seqs, enz)), (L, enz)
+
+
+def test_tuned_cpu_knn_equals_checker():
+    """oracle/gm_oracle.c gmo_knn_hamming_fast (the timed CPU arm: AVX-512 VPOPCNTD + query blocking) returns exactly
+    what the scalar checker gmo_knn returns, ties included, on ragged sizes"""
+    rng = np.random.default_rng(9)
+    for n_t, n_q, L, k in ((1, 3, 20, 2), (17, 70, 5, 5), (4097, 129, 20, 1), (50003, 777, 27, 32), (8192, 64, 1, 3)):
+        t = rng.integers(0, 1 << (2 * L), size=n_t, dtype=np.uint64)
+        q = np.concatenate([t[: min(n_t, n_q // 2)], rng.integers(0, 1 << (2 * L), size=n_q - min(n_t, n_q // 2), dtype=np.uint64)])
+        a, b = O.c_knn(t, q, L, 0, k), O.c_knn_hamming_fast(t, q, L, k)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (n_t, n_q, L, k)
