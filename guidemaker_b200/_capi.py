@@ -223,7 +223,7 @@ class Session:
         h, nu = _vp(), ctypes.c_int64()
         uniq = np.empty(self.n_rows, np.uint64); r2u = np.empty(self.n_rows, np.int32)
         _check(load_library().gm_session_index(self._h, int(metric), ctypes.byref(h), _p(uniq), _p(r2u), ctypes.byref(nu)), "gm_session_index")
-        return Index.from_handle(h, nu.value, self.L, metric), uniq[: nu.value].copy(), r2u
+        return Index.from_handle(h, nu.value, self.L, metric), uniq[: nu.value], r2u
 
     def knn(self, index: "Index", qmask: np.ndarray, k: int):
         qmask = np.ascontiguousarray(qmask, np.uint8 if qmask.dtype != np.bool_ else np.bool_).view(np.uint8)

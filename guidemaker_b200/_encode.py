@@ -94,6 +94,6 @@ def matrix_to_strings(mat: np.ndarray):
     """(N, W) uint8 -> pandas-ready string array without creating Python objects (Arrow buffers)."""
     import pyarrow as pa
     n, w = mat.shape
-    offsets = pa.py_buffer((np.arange(n + 1, dtype=np.int64) * w))
+    offsets = pa.py_buffer(np.arange(0, (n + 1) * w, w, dtype=np.int64) if w else np.zeros(n + 1, np.int64))
     data = pa.py_buffer(np.ascontiguousarray(mat))
     return pa.LargeStringArray.from_buffers(n, offsets, data)

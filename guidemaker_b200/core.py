@@ -89,11 +89,35 @@ class _PackedStash:
     """Packed guides riding along in ``DataFrame.attrs``.  pandas deep-copies ``attrs`` into every Series/frame derived
     from the frame (``__finalize__``); the stash is immutable, so copies share it instead of duplicating 8 bytes per
     row on every column access."""
-    __slots__ = ("crc", "shape", "guides", "session")
+    __slots__ = ("crc", "shape", "guides", "session", "mat", "addr")
 
-    def __init__(self, crc, shape, guides, session=None):
+    def __init__(self, crc, shape, guides, session=None, mat=None):
         self.crc, self.shape, self.guides, self.session = crc, tuple(shape), guides, session
         self.guides.setflags(write=False)
+        # The `target` column is an Arrow array built zero-copy over `mat`: Arrow buffers are immutable, so a column
+        # whose data buffer still lives at this address IS this column -- an O(1) identity check; the CRC (lazy) is
+        # only needed for frames whose column was rebuilt.
+        self.mat = mat
+        self.addr = None if mat is None else mat.ctypes.data
+        if mat is not None:
+            mat.setflags(write=False)
+
+    def matches_column(self, col) -> bool:
+        """True iff `col` (a pandas str Series) is backed by the very Arrow buffer this stash was made for"""
+        try:
+            arr = col.array._pa_array
+            if arr.num_chunks != 1:
+                return False
+            c = arr.chunk(0)
+            return (self.addr is not None and len(c) == self.shape[0] and c.offset == 0 and c.null_count == 0
+                    and c.buffers()[2].address == self.addr and c.buffers()[2].size == self.shape[0] * self.shape[1])
+        except Exception:  # noqa: BLE001
+            return False
+
+    def crc32(self):
+        if self.crc is None:
+            self.crc = zlib.crc32(self.mat)
+        return self.crc
 
     def __deepcopy__(self, memo):
         return self
@@ -179,7 +203,7 @@ class PamTarget:
         # The packed guides and the session ride along so that TargetProcessor need not re-encode / re-upload n strings;
         # they are used only if the CRC of the `target` column's bytes still matches (any edit, filter or reorder of the
         # frame voids them).
-        df.attrs["_gm_packed"] = _PackedStash(zlib.crc32(target_mat), target_mat.shape, guides, sess)
+        df.attrs["_gm_packed"] = _PackedStash(None, target_mat.shape, guides, sess, mat=target_mat)
         return df
 
     @staticmethod
@@ -278,17 +302,24 @@ class TargetProcessor:
         key = (id(self.targets), id(col.array), len(col))
         cache = getattr(self, "_packed_cache", None)
         if cache is None or cache[0] != key:
-            mat = self._guide_matrix()
             stash = self.targets.attrs.get("_gm_packed") if isinstance(self.targets.attrs, dict) else None
-            if (isinstance(stash, _PackedStash) and tuple(stash.shape) == mat.shape and len(stash.guides) == len(mat)
-                    and stash.crc == zlib.crc32(np.ascontiguousarray(mat))):
-                guides = stash.guides                          # produced by find_targets for exactly these strings
-                sess = stash.session
+            if isinstance(stash, _PackedStash) and stash.matches_column(col):
+                mat, guides, sess = stash.mat, stash.guides, stash.session      # the very column find_targets built
             else:
-                guides, sess = encode_matrix(mat), None
-            cache = (key, guides, mat.shape[1], col.array, sess)     # keep the array alive: ids stay unique
+                mat = self._guide_matrix()
+                if (isinstance(stash, _PackedStash) and stash.mat is not None and tuple(stash.shape) == mat.shape
+                        and stash.crc32() == zlib.crc32(np.ascontiguousarray(mat))):
+                    guides, sess = stash.guides, stash.session                  # rebuilt column, same strings
+                else:
+                    guides, sess = encode_matrix(mat), None
+            cache = (key, guides, mat.shape[1], col.array, sess, mat)           # keep the array alive: ids stay unique
             self._packed_cache = cache
         return cache[1], cache[2]
+
+    def _matrix(self) -> np.ndarray:
+        """(N, L) ASCII matrix of the `target` column (cached with the packed guides)"""
+        self._packed()
+        return self._packed_cache[5]
 
     def _session(self):
         """the device-resident scan these rows came from (``find_targets``), or None if the frame was edited since"""
@@ -323,8 +354,10 @@ class TargetProcessor:
         """seedseq = PAM-proximal ``lsr`` nt; isseedduplicated = keep-first duplicate flag (core.py:388-416)."""
         guides, _ = self._packed()
         sess = self._session()
-        self.targets = deepcopy(self.targets)
-        mat = self._guide_matrix()
+        mat = self._matrix()
+        # The reference deep-copies the frame (core.py:414) so that the caller's frame keeps its columns; only two
+        # columns are REPLACED below, so a shallow copy gives the same isolation without copying ~0.5 GB of strings.
+        self.targets = self.targets.copy(deep=False)
         L = mat.shape[1]
         five = bool(self.pam_orientation)
         lsr = int(self.lsr)
@@ -341,7 +374,7 @@ class TargetProcessor:
         lsr_key = lsr_eff if lsr_eff < L else 0
         self.targets['isseedduplicated'] = sess.seed_dedup(lsr_key) if sess is not None else _capi.seed_dedup(guides, L, lsr_key, five)
         col = self.targets['target']
-        self._packed_cache = ((id(self.targets), id(col.array), len(col)), guides, L, col.array, sess)
+        self._packed_cache = ((id(self.targets), id(col.array), len(col)), guides, L, col.array, sess, mat)
 
     def create_index(self, configpath: str, num_threads=2):
         """Upload the distinct guides to the GPU (replaces the HNSW build, core.py:418-467).
@@ -380,7 +413,7 @@ class TargetProcessor:
         qmask = ((t['isseedduplicated'] == False) | (t['hasrestrictionsite'] == False)).to_numpy(dtype=bool)  # noqa: E712
         guides, L = self._packed()
         sess = self._session()
-        q = np.ascontiguousarray(guides[qmask])
+        q = guides if qmask.all() else np.ascontiguousarray(guides[qmask])
         index = self.nmslib_index
         index.setQueryTimeParams({'efSearch': ef})
         if len(q) == 0:
@@ -396,7 +429,8 @@ class TargetProcessor:
         group = None
         r2u = getattr(self, "_row2uniq", None)
         if r2u is not None and r2u[0] == self._packed_cache[0] and len(r2u[1]) == len(guides) and index.uniq is self.nmslib_index.uniq:
-            group = r2u[1][np.flatnonzero(qmask)[rows]]
+            qgroup = r2u[1] if len(q) == len(guides) else r2u[1][qmask]       # distinct-guide id of every query row
+            group = qgroup if len(rows) == len(q) else qgroup[rows]
         self.neighbors = NeighborMap(q, idx, dist, index.uniq, L, group=group, rows=rows)
 
     def export_bed(self) -> object:

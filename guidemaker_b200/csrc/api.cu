@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <chrono>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 
@@ -42,6 +44,23 @@ double now_ms() {
 }
 void trace(const char *what, double t0_ms) {
     if (trace_on()) fprintf(stderr, "[gm_trace] %-28s %9.3f ms\n", what, now_ms() - t0_ms);
+}
+void prefault(void *p, size_t bytes) {
+    if (!p || bytes < (8u << 20)) return;
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt == 0 ? 4 : (nt > 16 ? 16 : nt);
+    const size_t page = 4096, slice = ((bytes / nt) + page - 1) / page * page;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) {
+        const size_t lo = (size_t)t * slice, hi = lo + slice < bytes ? lo + slice : bytes;
+        if (lo >= hi) break;
+        th.emplace_back([=]() {
+            volatile char *c = (volatile char *)p;
+            for (size_t o = lo; o < hi; o += page) c[o] = 0;
+            c[hi - 1] = 0;
+        });
+    }
+    for (auto &x : th) x.join();
 }
 int device_sm_count() { return g_sm_count; }
 bool initialised() { return g_device >= 0; }

@@ -47,6 +47,12 @@ int ensure_init();
 inline cudaError_t dev_alloc(void **p, size_t bytes, cudaStream_t st) { return cudaMallocAsync(p, bytes ? bytes : 16, st); }
 inline void dev_free(void *p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
 
+// Touch every page of a host OUTPUT buffer with several threads before a large device->host copy lands in it.  A fresh
+// numpy array is untouched virtual memory: the copy's destination pages are then faulted in (and zero-filled by the
+// kernel) one at a time by the single thread that drives the copy -- measured on the B200 box: 512 MB device->host takes
+// 255 ms into untouched memory, 26 ms into touched memory (tools/probes/alloc_probe.cu).  Faulting scales with threads.
+void prefault(void *p, size_t bytes);
+
 // GM_TRACE=1 prints wall-clock per host-side phase of the host-buffer entry points
 bool trace_on();
 double now_ms();

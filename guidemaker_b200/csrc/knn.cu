@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(THREADS) knn_hamming_scan_kernel(const ScanArg
         tau[r] = qi < a.q ? t : 0u;                           // padding queries never insert
         C[r] = bias_of(tau[r]);
     }
-    uint32_t *const my_lists = a.lists + ((size_t)blockIdx.y * a.q_pad + qbase) * a.k;
+    uint32_t *const my_lists = a.lists + ((size_t)blockIdx.y * a.list_stride + (qbase - a.list_q0)) * a.k;
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; s++) mbar_init(&s_full[s], 1);
@@ -138,6 +138,23 @@ __global__ void __launch_bounds__(THREADS) knn_hamming_scan_kernel(const ScanArg
 }
 
 // ---- K4: Levenshtein pair scan (Myers bit-parallel, one 32-bit word per pair) -------------------------
+// Myers' recurrence in Hyyro's global-alignment form (distance.cuh: myers_planes) with the roles arranged for the SIMT
+// machine: the query is the pattern (its L rows live in one 32-bit word per thread), the target is the text and is
+// WARP-UNIFORM.  The match vector of a step, Eq = "pattern rows equal to text base j", is then one of four per-query
+// constants PM[A|C|G|T] chosen by a value every lane agrees on -- so the choice is a uniform branch, not arithmetic:
+// the step body exists four times (once per text base) and costs 7 LOP3 + 3 IMAD per pair, against 10 LOP3 + 3 IMAD (+ the
+// broadcast of the text bit planes) when Eq is recomputed from the planes.  The ALU pipe (LOP3) is what bounds the kernel.
+#define GM_MYERS_STEP(EQ)                                                                                    \
+    _Pragma("unroll") for (int r = 0; r < R; r++) {                                                          \
+        const uint32_t Eq = (EQ)[r];                                                                         \
+        const uint32_t Xv = Eq | Mv[r];                                                                      \
+        const uint32_t Xh = (((Eq & Pv[r]) + Pv[r]) ^ Pv[r]) | Eq;                                           \
+        const uint32_t Ph = (Mv[r] | ~(Xh | Pv[r])) * two + 1u;      /* (Ph << 1) | 1 as ONE multiply-add */  \
+        const uint32_t Mh = (Pv[r] & Xh) * two;                                                              \
+        Pv[r] = Mh | ~(Xv | Ph);                                                                             \
+        Mv[r] = Ph & Xv;                                                                                     \
+    }
+
 template <int R>
 __global__ void __launch_bounds__(THREADS) knn_leven_scan_kernel(const ScanArgs a) {
     __shared__ __align__(128) uint2 s_t[NSTAGE][CHUNK];
@@ -150,19 +167,24 @@ __global__ void __launch_bounds__(THREADS) knn_leven_scan_kernel(const ScanArgs 
 
     const int L = a.L;
     const uint32_t lmask = (1u << L) - 1u;
+    // The shifts of the recurrence run as multiply-adds on the FMA pipe (x * 2 + 1, x * 2), which has spare issue slots;
+    // `two` is opaque to the compiler (L <= 27), otherwise it turns them back into an add plus a LOP3 on the ALU pipe.
+    const uint32_t two = 2u + ((uint32_t)L >> 30);
     const int64_t qbase = (int64_t)blockIdx.x * (THREADS * R) + tid;
-    uint32_t qlo[R], qhi[R], tau[R];
+    uint32_t pmA[R], pmC[R], pmG[R], pmT[R], tau[R];       // bits >= L hold garbage that never flows downwards
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int64_t qi = qbase + (int64_t)r * THREADS;
         const uint2 p = a.qplanes[qi];
-        qlo[r] = p.x;
-        qhi[r] = p.y;
+        pmA[r] = ~(p.x | p.y);
+        pmC[r] = p.x & ~p.y;
+        pmG[r] = p.y & ~p.x;
+        pmT[r] = p.x & p.y;
         uint32_t t = 31u;
         if (a.warm) t = min((a.warm[(size_t)qi * a.k + (a.k - 1)] >> IDX_BITS) + 1u, 31u);
         tau[r] = qi < a.q ? t : 0u;
     }
-    uint32_t *const my_lists = a.lists + ((size_t)blockIdx.y * a.q_pad + qbase) * a.k;
+    uint32_t *const my_lists = a.lists + ((size_t)blockIdx.y * a.list_stride + (qbase - a.list_q0)) * a.k;
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; s++) mbar_init(&s_full[s], 1);
@@ -183,25 +205,19 @@ __global__ void __launch_bounds__(THREADS) knn_leven_scan_kernel(const ScanArgs 
 
         for (int g = 0; g < n_here; g++) {
             const uint2 t = s_t[stage][g];                  // warp-uniform target
+            // text bases, 2 bits each, in step order: base j = (code >> 2j) & 3 (A=0 C=1 G=2 T=3)
+            uint64_t code = spread_bits(t.x) | (spread_bits(t.y) << 1);
             uint32_t Pv[R], Mv[R];
 #pragma unroll
             for (int r = 0; r < R; r++) { Pv[r] = 0xFFFFFFFFu; Mv[r] = 0u; }
 #pragma unroll 1
             for (int j = 0; j < L; j++) {
-                const uint32_t LO = 0u - ((t.x >> j) & 1u);  // uniform across the warp
-                const uint32_t HI = 0u - ((t.y >> j) & 1u);
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const uint32_t Eq = ~((qlo[r] ^ LO) | (qhi[r] ^ HI));
-                    const uint32_t Xv = Eq | Mv[r];
-                    const uint32_t Xh = (((Eq & Pv[r]) + Pv[r]) ^ Pv[r]) | Eq;
-                    uint32_t Ph = Mv[r] | ~(Xh | Pv[r]);
-                    uint32_t Mh = Pv[r] & Xh;
-                    Ph = (Ph << 1) | 1u;
-                    Mh = Mh << 1;
-                    Pv[r] = Mh | ~(Xv | Ph);
-                    Mv[r] = Ph & Xv;
-                }
+                const uint32_t base = (uint32_t)code & 3u;   // the same in every lane: the switch is a uniform branch
+                code >>= 2;
+                if (base == 0u) { GM_MYERS_STEP(pmA) }
+                else if (base == 1u) { GM_MYERS_STEP(pmC) }
+                else if (base == 2u) { GM_MYERS_STEP(pmG) }
+                else { GM_MYERS_STEP(pmT) }
             }
 #pragma unroll
             for (int r = 0; r < R; r++) {
@@ -219,20 +235,28 @@ __global__ void __launch_bounds__(THREADS) knn_leven_scan_kernel(const ScanArgs 
         if (++stage == NSTAGE) { stage = 0; parity ^= 1u; }
     }
 }
+#undef GM_MYERS_STEP
 
 // ---- merge: k smallest keys over the splits of each query ------------------------------------------------
+// Queries below `tail_q0` have `splits` lists in `lists` ([split][q_pad][k]); the others (K3b's split tail wave) have
+// `tail_splits` lists in `tail_lists` ([split][tail_stride][k], row = query - tail_q0).
 __global__ void knn_merge_kernel(const uint32_t *__restrict__ lists, int splits, int64_t q, int64_t q_pad, int k,
+                                 const uint32_t *__restrict__ tail_lists, int tail_splits, int64_t tail_q0, int64_t tail_stride,
                                  int32_t *__restrict__ out_idx, uint8_t *__restrict__ out_dist, int dist_only) {
     const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= q) return;
+    const bool tail = qi >= tail_q0;
+    const uint32_t *base = tail ? tail_lists + (size_t)(qi - tail_q0) * k : lists + (size_t)qi * k;
+    const size_t stride = (size_t)(tail ? tail_stride : q_pad) * k;
+    const int ns = tail ? tail_splits : splits;
     uint8_t ptr[MAX_SPLITS];
-    for (int s = 0; s < splits; s++) ptr[s] = 0;
+    for (int s = 0; s < ns; s++) ptr[s] = 0;
     for (int j = 0; j < k; j++) {
         uint32_t best = KEY_EMPTY;
         int bs = -1;
-        for (int s = 0; s < splits; s++) {
+        for (int s = 0; s < ns; s++) {
             if (ptr[s] < k) {
-                const uint32_t v = lists[((size_t)s * q_pad + qi) * k + ptr[s]];
+                const uint32_t v = base[(size_t)s * stride + ptr[s]];
                 if (v < best) { best = v; bs = s; }
             }
         }
@@ -276,7 +300,7 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     GM_ARG(d_q && d_dist && (dist_only || d_idx), "gm_knn: NULL buffer");
 
     // queries per thread: Levenshtein keeps 2 more state words per pair, so it uses R=4
-    const int R = ix->metric == GM_METRIC_HAMMING ? (g_tune_r == 4 ? 4 : 8) : 4;
+    const int R = ix->metric == GM_METRIC_HAMMING ? (g_tune_r == 4 ? 4 : 8) : (g_tune_r == 4 ? 4 : 8);
     const bool use_tc = g_tune_engine == 1 && ix->metric == GM_METRIC_HAMMING;
     const int QT = THREADS * R;
     const int64_t tiles = (q + QT - 1) / QT;
@@ -328,15 +352,20 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
         tail_splits = (scan_chunks + tail_cps - 1) / tail_cps;
         if (tail_splits < 2) { tail_tiles = 0; tail_splits = 1; }
     }
-    const int list_splits = tail_tiles ? tail_splits : splits;          // split lists per query that memset / merge see
-
+    // lists: [splits][q_pad][k] for the main launch; the split tail wave of K3b keeps its own compact
+    // [tail_splits][tail_q][k] block behind it (only the tail's queries have more than one list)
+    const int64_t tail_q = (int64_t)tail_tiles * (use_tc ? tc_query_tile() : 0);
+    const int64_t tail_q0 = tail_tiles ? q_pad - tail_q : q_pad;
     const size_t qp_bytes = (size_t)q_pad * sizeof(uint2);
-    const size_t list_bytes = (size_t)list_splits * q_pad * k * sizeof(uint32_t);
+    const size_t main_bytes = (size_t)splits * q_pad * k * sizeof(uint32_t);
+    const size_t tail_bytes = (size_t)(tail_tiles ? tail_splits : 0) * tail_q * k * sizeof(uint32_t);
+    const size_t list_bytes = main_bytes + tail_bytes;
     const size_t warm_bytes = warm ? (size_t)q_pad * k * sizeof(uint32_t) : 0;
     int rc = ensure_ws(ix, qp_bytes + list_bytes + warm_bytes, st);
     if (rc) return rc;
     uint2 *qplanes = reinterpret_cast<uint2 *>(ix->ws);
     uint32_t *lists = reinterpret_cast<uint32_t *>((char *)ix->ws + qp_bytes);
+    uint32_t *tlists = reinterpret_cast<uint32_t *>((char *)ix->ws + qp_bytes + main_bytes);
     uint32_t *wlists = warm ? reinterpret_cast<uint32_t *>((char *)ix->ws + qp_bytes + list_bytes) : nullptr;
 
     to_planes_kernel<<<(unsigned)((q_pad + 255) / 256), 256, 0, st>>>(d_q, q, q_pad, qplanes);
@@ -354,6 +383,8 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     a.q_pad = q_pad;
     a.k = k;
     a.L = ix->L;
+    a.list_stride = q_pad;
+    a.list_q0 = 0;
     a.dbg = nullptr;
     static unsigned long long *d_dbg = nullptr;
     const char *dbg_env = getenv("GM_TC_DEBUG");
@@ -387,6 +418,9 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
         if (tail_tiles) {                                           // the last query tiles, split to fill one short wave
             a.tile_offset = (int)grid_x - tail_tiles;
             a.chunks_per_split = tail_cps;
+            a.lists = tlists;
+            a.list_stride = tail_q;
+            a.list_q0 = tail_q0;
             rc = launch_hamming_tc(dim3((unsigned)tail_tiles, (unsigned)tail_splits), st, a);
             if (rc) return rc;
         }
@@ -397,7 +431,7 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
             // (the counters are compiled in with -DGM_TC_STATS, see tools/tc_ablate.py; otherwise they read 0)
             fprintf(stderr, "[tc_dbg] candidate events %llu (%.2f per query), list inserts %llu (%.2f per query), grid %u x %d; "
                     "epilogue warps: %.1f %% of their time behind a full candidate queue (%llu stalls)\n", h[0],
-                    (double)h[0] / (double)q, h[1], (double)h[1] / (double)q, (unsigned)(q_pad / tc_query_tile()), list_splits,
+                    (double)h[0] / (double)q, h[1], (double)h[1] / (double)q, (unsigned)(q_pad / tc_query_tile()), tail_tiles ? tail_splits : splits,
                     h[4] ? 100.0 * (double)h[2] / (double)h[4] : 0.0, h[3]);
             fprintf(stderr, "[tc_dbg] cycles per tile over successive 256-tile windows of CTA 200:");
             for (int w = 1; w < 48 && h[8 + w]; w++) fprintf(stderr, " %.0f", (double)(h[8 + w] - h[8 + w - 1]) / 256.0);
@@ -408,7 +442,8 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     pairs += (double)q * ((double)ix->n_u - (double)first_chunk * CHUNK);
     prof_end(slot, st, pairs);
 
-    knn_merge_kernel<<<(unsigned)((q + 127) / 128), 128, 0, st>>>(lists, list_splits, q, q_pad, k, d_idx, d_dist, dist_only);
+    knn_merge_kernel<<<(unsigned)((q + 127) / 128), 128, 0, st>>>(lists, splits, q, q_pad, k, tlists, tail_splits, tail_q0, tail_q, d_idx, d_dist,
+                                                                  dist_only);
     count_launch();
     GM_CUDA(cudaGetLastError());
     return GM_OK;
@@ -545,6 +580,8 @@ static int knn_host(void *index, const uint64_t *q2bit, int64_t q, int k, int32_
         trace("knn: launch", t0);
         if (rc == GM_OK) {
             t0 = now_ms();
+            if (!dist_only) prefault(out_idx, nd * sizeof(int32_t));        // overlaps the kernels enqueued above
+            prefault(out_dist, nd);
             if (!dist_only) e = cudaMemcpyAsync(out_idx, d_idx, nd * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess) e = cudaMemcpyAsync(out_dist, d_dist, nd, cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);

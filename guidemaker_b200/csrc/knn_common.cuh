@@ -61,7 +61,9 @@ struct ScanArgs {
     const uint2 *qplanes;
     int64_t q, q_pad;
     int k;
-    uint32_t *lists;          // [gridDim.y][q_pad][k]
+    uint32_t *lists;          // [gridDim.y][list_stride][k]; row of query qi = qi - list_q0
+    int64_t list_stride;      // queries per split in `lists` (q_pad, or the tail's query count for K3b's tail launch)
+    int64_t list_q0;          // first query stored in `lists`
     const uint32_t *warm;     // [q_pad][k] lists of the warm-up launch or nullptr
     int L;
     unsigned long long *dbg;  // optional per-role cycle counters of block (0,0) (GM_TC_DEBUG=1), else nullptr

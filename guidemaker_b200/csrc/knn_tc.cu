@@ -68,7 +68,10 @@ namespace gm {
 static constexpr int TC_M = 128;           // rows per A operand
 static constexpr int TC_N = 128;           // targets per tile
 static constexpr int TC_SETS = 2;          // A operands (query tiles) per CTA
-static constexpr int TC_STAGES = 6;        // B tiles in shared memory (even: a stage always serves the same producer group)
+#ifndef GM_TC_STAGES
+#define GM_TC_STAGES 6
+#endif
+static constexpr int TC_STAGES = GM_TC_STAGES;   // B tiles in shared memory (even: a stage always serves the same producer group)
 static constexpr int TC_QT = 256 * TC_SETS;                        // queries per CTA
 static constexpr int TC_EPI_WARPS = 8 * TC_SETS;                   // (set, buffer, quadrant)
 static constexpr int TC_PROD_WARP0 = TC_EPI_WARPS;
@@ -575,7 +578,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
     tc_fence_before();
     __syncthreads();
     if (tid < TC_QT) {                                              // publish the finished lists
-        uint32_t *dst = a.lists + ((size_t)blockIdx.y * a.q_pad + (size_t)(qbase + tid)) * a.k;
+        uint32_t *dst = a.lists + ((size_t)blockIdx.y * a.list_stride + (size_t)(qbase + tid - a.list_q0)) * a.k;
         for (int j = 0; j < a.k; j++) dst[j] = s_lists[j * TC_QT + tid];
     }
     if (warp == TC_MMA_WARP) tc_dealloc(tmem, 512);

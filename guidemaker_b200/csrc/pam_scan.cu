@@ -605,6 +605,7 @@ extern "C" int gm_session_fetch_rows(void *session, uint64_t *guide2bit, uint32_
     const size_t nt = (size_t)(s->n_fwd + s->n_rev);
     if (nt == 0) return GM_OK;
     const double t0 = now_ms();
+    prefault(guide2bit, nt * 8); prefault(start, nt * 4); prefault(pamcode, nt * 2); prefault(rec, nt * 4); prefault(strand, nt);
     if (guide2bit) GM_CUDA(cudaMemcpyAsync(guide2bit, s->guides, nt * 8, cudaMemcpyDeviceToHost, 0));
     if (start) GM_CUDA(cudaMemcpyAsync(start, s->start, nt * 4, cudaMemcpyDeviceToHost, 0));
     if (pamcode) GM_CUDA(cudaMemcpyAsync(pamcode, s->pamcode, nt * 2, cudaMemcpyDeviceToHost, 0));
@@ -624,6 +625,7 @@ extern "C" int gm_session_fetch_text(void *session, uint8_t *target_ascii, uint8
     const double t0 = now_ms();
     int rc = ensure_comp_table();
     if (rc) return rc;
+    trace("  text: complement table", t0);
     uint8_t *d_t = nullptr, *d_c = nullptr, *d_e = nullptr;
     cudaError_t e = cudaSuccess;
     if (target_ascii) {
@@ -631,6 +633,9 @@ extern "C" int gm_session_fetch_text(void *session, uint8_t *target_ascii, uint8
         if (e == cudaSuccess) {
             decode_rows_kernel<<<(unsigned)((nt * s->L + 255) / 256), 256>>>(s->guides, nt, s->L, d_t);
             count_launch();
+            if (trace_on()) { cudaStreamSynchronize(0); trace("  text: decode kernel", t0); }
+            prefault(target_ascii, (size_t)nt * s->L);
+            trace("  text: prefault target", t0);
             e = cudaMemcpyAsync(target_ascii, d_t, (size_t)nt * s->L, cudaMemcpyDeviceToHost, 0);
         }
     }
@@ -641,6 +646,10 @@ extern "C" int gm_session_fetch_text(void *session, uint8_t *target_ascii, uint8
             context_rows_kernel<<<(unsigned)((nt * width + 255) / 256), 256>>>(s->seq, s->rec_start, s->start, s->rec, s->strand, nt, s->P, s->L,
                                                                                s->five_prime, width, d_c, d_e);
             count_launch();
+            if (trace_on()) { cudaStreamSynchronize(0); trace("  text: + D2H target, context kernel", t0); }
+            prefault(context, (size_t)nt * width);
+            prefault(edge, (size_t)nt);
+            trace("  text: prefault context", t0);
             e = cudaMemcpyAsync(context, d_c, (size_t)nt * width, cudaMemcpyDeviceToHost, 0);
             if (e == cudaSuccess && edge) e = cudaMemcpyAsync(edge, d_e, (size_t)nt, cudaMemcpyDeviceToHost, 0);
         }

@@ -103,6 +103,7 @@ extern "C" int gm_session_index(void *session, int metric, void **index, uint64_
     cudaError_t e = cudaSuccess;
     if (!s->first32) e = dev_alloc((void **)&s->first32, (size_t)n * 4, st);
     if (e == cudaSuccess) rc = dedup_dev(s->guides, n, GM_MAX_L, 0, 0, nullptr, nullptr, s->first32, st);
+    if (trace_on()) { cudaStreamSynchronize(st); trace("  index: first occurrence", t0); }
     if (rc == GM_OK && e == cudaSuccess) e = dev_alloc((void **)&d_flag, (size_t)(n + 1) * 4, st);
     if (rc == GM_OK && e == cudaSuccess) e = dev_alloc((void **)&d_rank, (size_t)(n + 1) * 4, st);
     if (rc == GM_OK && e == cudaSuccess) e = dev_alloc((void **)&d_r2u, (size_t)n * 4, st);
@@ -122,9 +123,13 @@ extern "C" int gm_session_index(void *session, int metric, void **index, uint64_
         if (e == cudaSuccess) e = cudaMemcpyAsync(&last[1], d_flag + (n - 1), 4, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     }
+    trace("  index: + compaction", t0);
     const int64_t nu = (int64_t)last[0] + last[1];
     if (rc == GM_OK && e == cudaSuccess) {
         rc = gm_index_create_dev(d_uniq, nu, s->L, metric, index, st);
+        if (trace_on()) { cudaStreamSynchronize(st); trace("  index: + planes", t0); }
+        prefault(uniq2bit, (size_t)nu * 8);
+        prefault(row2uniq, (size_t)n * 4);
         if (rc == GM_OK && uniq2bit) e = cudaMemcpyAsync(uniq2bit, d_uniq, (size_t)nu * 8, cudaMemcpyDeviceToHost, st);
         if (rc == GM_OK && e == cudaSuccess && row2uniq) e = cudaMemcpyAsync(row2uniq, d_r2u, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -185,6 +190,8 @@ static int session_knn(void *session, void *index, const uint8_t *qmask, int64_t
     }
     if (rc == GM_OK && e == cudaSuccess) rc = gm_knn_dev(index, d_q, cnt, k, d_idx, d_dist, st);
     if (rc == GM_OK && e == cudaSuccess && !device_out) {
+        prefault(out_idx, (size_t)n_q * k * 4);                    // overlaps the kernels enqueued above
+        prefault(out_dist, (size_t)n_q * k);
         e = cudaMemcpyAsync(out_idx, d_idx, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(out_dist, d_dist, (size_t)n_q * k, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -81,14 +81,19 @@ class NeighborMap(Mapping):
         without it, one stable sort.  The big arrays are gathered once, with the composed index."""
         if rows is None:
             rows = np.arange(len(qcodes), dtype=np.int64)
-        codes = qcodes[rows]
-        n = len(codes)
+        n = len(rows)
+        all_rows = n == len(qcodes)
         if group is not None and n:
-            slot = np.full(len(uniq) if len(uniq) else 1, -1, dtype=np.int64)
-            rev = np.arange(n - 1, -1, -1, dtype=np.int64)
-            slot[np.asarray(group)[rev]] = rev               # repeated index: the last assignment wins = smallest row
-            kept = np.flatnonzero(slot[group] == np.arange(n))
+            # first kept row of every distinct guide, linear: rows are written in DESCENDING order, so the last
+            # assignment to a slot -- the smallest row -- wins; only slots that are read back are ever written
+            group = np.asarray(group)
+            it = np.int32 if n < (1 << 31) else np.int64
+            rev = np.arange(n - 1, -1, -1, dtype=it)
+            slot = np.empty(int(group.max()) + 1 if len(uniq) == 0 else len(uniq), dtype=it)
+            slot[group[::-1]] = rev
+            kept = np.flatnonzero(slot[group] == np.arange(n, dtype=it))
         else:
+            codes = qcodes if all_rows else qcodes[rows]
             order = np.argsort(codes, kind="stable")
             srt = codes[order]
             head = np.ones(n, dtype=bool)
@@ -96,9 +101,9 @@ class NeighborMap(Mapping):
             keep_mask = np.zeros(n, dtype=bool)
             keep_mask[order[head]] = True                    # stable sort: smallest row of each group
             kept = np.flatnonzero(keep_mask)
-        final = rows[kept]
+        final = kept if all_rows else rows[kept]
         whole = len(final) == len(qcodes)                    # nothing dropped: no copy at all
-        self.codes = np.ascontiguousarray(qcodes if whole else codes[kept])
+        self.codes = np.ascontiguousarray(qcodes if whole else qcodes[final])
         self.idx = idx if whole else idx[final]
         self.dist = dist if whole else dist[final]
         self.uniq, self.L = uniq, int(L)

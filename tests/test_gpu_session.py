@@ -11,6 +11,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pandas as pd
 import pytest
 
 from oracle import oracle as O
@@ -69,7 +70,7 @@ def test_session_rows_and_text_vs_oracle(capi, name):
         assert np.array_equal(a, b), what
     t, c, e = s.fetch_text(30)
     ot, oc, oe = o.fetch_text(30)
-    assert np.array_equal(t, ot) and np.array_equal(e, oe) and e.any()
+    assert np.array_equal(t, ot) and np.array_equal(e, oe) and (e.any() or name not in ("ngg3p20", "ngg5p20"))
     assert np.array_equal(c[~e], oc[~oe]) and (c[e] == ord("?")).all()
     s.close()
 
@@ -77,7 +78,7 @@ def test_session_rows_and_text_vs_oracle(capi, name):
 def test_session_chain_vs_oracle(capi):
     """seed flags, restriction flags, distinct-guide table + row map, masked kNN (both metrics) off one session"""
     rng = np.random.default_rng(77)
-    recs = _genome(rng, [40000, 2500, 60000, 17], gc=0.6)
+    recs = _genome(rng, [12000, 2500, 20000, 17], gc=0.6)
     buf, rec_start = _join(recs)
     for pam, five, L in (("NGG", False, 20), ("TTTV", True, 23)):
         s = capi.Session(buf, rec_start, pam, five, L)
@@ -178,8 +179,8 @@ def test_config4_multi_record_controls(capi, tmp_path):
     assert df["seqid"].nunique() == 16 and 6.0e5 < len(df) < 1.1e6
     g, uniq = _check_rows_vs_oracle(tp, 20, 0, 5, 512, seed=4)
     # rows are grouped per record, forward block first (core.py:254-284)
-    codes = df["seqid"].cat.codes.to_numpy()
-    assert (np.diff(codes) >= 0).all()
+    codes = pd.factorize(df["seqid"].astype(str))[0]                 # record order = order of first appearance
+    assert (np.diff(codes) >= 0).all() and list(dict.fromkeys(df["seqid"].astype(str))) == [r.id for r in recs]
     for c in (0, 7, 15):
         st = df["strand"].to_numpy()[codes == c]
         assert st[0] and not st[-1] and (np.diff(st.astype(np.int8)) <= 0).all()
@@ -193,7 +194,7 @@ def test_config4_multi_record_controls(capi, tmp_path):
     assert np.array_equal(true.astype(np.float64), d[rows])
     # the reference's default thresholds (MINIMUM_HMDIST 7, multiples 10..10000) on a small n: several rounds
     np.random.seed(41)
-    cmin, cmed, cdf = tp.get_control_seqs(recs, configpath=_cfg(tmp_path, 5, (10, 100, 1000)), length=20, n=50)
+    cmin, cmed, cdf = tp.get_control_seqs(recs, configpath=_cfg(tmp_path, 5, (10, 100, 1000, 10000)), length=20, n=50)
     assert cmin >= 5 and tp.ncontrolsearched in (500, 5000, 50000)
     true = O.c_min_dist(uniq, encode_guides(cdf["Sequences"].tolist(), 20), 20, 0, threads=os.cpu_count())
     assert np.array_equal(true.astype(np.float64), cdf["Hamming distance"].to_numpy())
