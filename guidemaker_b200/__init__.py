@@ -5,7 +5,7 @@ Drop-in for the hot-path surface of ``guidemaker.core`` (``PamTarget.find_target
 see DESIGN.md and INTEGRATION.md.  All arithmetic runs in ``lib/libgm_b200.so`` (hand-written
 sm_100a CUDA behind the C ABI of ``include/gm_b200.h``); there is no CPU fallback.
 """
-from .core import PamTarget, TargetProcessor, extend_ambiguous_dna  # noqa: F401
+from .core import Annotation, PamTarget, TargetProcessor, cfd_score, extend_ambiguous_dna  # noqa: F401
 
-__all__ = ["PamTarget", "TargetProcessor", "extend_ambiguous_dna", "core"]
+__all__ = ["PamTarget", "TargetProcessor", "Annotation", "cfd_score", "extend_ambiguous_dna", "core"]
 __version__ = "0.1.0"

@@ -52,6 +52,7 @@ _SIGS = {
     "gm_session_knn": [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp],
     "gm_session_knn_dev": [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp],
     "gm_session_free": [_vp],
+    "gm_cfd_scores": [_vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _vp, _vp],
     "gm_restriction_scan": [_vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp],
     "gm_restriction_scan_dev": [_vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp],
     "gm_index_create": [_vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)],

@@ -10,14 +10,26 @@ Same class, method names, attributes and column names as the reference:
     _format_guide_table       core.py:888-948   (vectorised: no per-row ``.apply``)
     _filterlocus / locuslen   core.py:950-983
 
-The nearest-feature join is a sorted-interval search (``numpy.searchsorted``), restating bedtools' documented
-``closest`` semantics: distance 0 for overlapping intervals, gap + 1 otherwise (book-ended intervals are 1 apart);
-``-D a`` signs the distance by the GUIDE's strand (negative = the feature lies upstream of the guide); ``-id`` ignores
-features downstream of the guide; ``-fd`` prefers the downstream feature when an upstream and a downstream one tie;
-``-t first`` takes the first of several equally close features in sorted (chrom, start) order; a guide on a contig
-without (eligible) features gets ``.``/-1 columns.  bedtools itself cannot be run here, so this restatement is pinned by
-the reference's own known answers (``tests/test_core.py:169-201``: 182 CDS, 7 qualifier keys, ``nearby.shape ==
-(7074, 12)``) and by hand-computed fixtures (tests/test_annotation.py) -- not by bedtools output.
+The nearest-feature join is a sorted-interval search (``numpy.searchsorted``) restating what the reference's two
+``bedtools closest`` calls deliver IN THE REFERENCE'S PIPELINE:
+
+* both BED frames have FIVE columns (chrom, start, end, name, strand), so bedtools reads the strand letters as the
+  BED *score* column and treats every interval as unstranded: ``-D a`` orients everything as if the guide were on
+  the + strand (upstream = lower coordinates) whatever the guide's real strand is;
+* ``-d -fd -D a -t first`` ("downstream" frame): the first feature DOWNSTREAM of the guide -- the nearest feature that
+  starts at or behind the guide's end; overlapping and upstream features are not candidates; distance = gap + 1 > 0;
+* ``-d -id -D a -t first`` ("upstream" frame): downstream features are ignored -- an overlapping feature (distance 0,
+  the first one in sorted order) or else the nearest feature that ends at or before the guide's start (distance
+  -(gap + 1) < 0);
+* a guide without an eligible feature gets ``.``/-1 columns (one output row per guide and frame either way).
+
+bedtools itself cannot be run here.  The semantics above were pinned against the reference's own known answers on
+Carsonella (``tests/test_core.py:183-246``): of the 16 combinations of {strand-aware | strand-blind} x {downstream frame
+keeps | drops overlaps} x {upstream frame keeps | drops overlaps} x {downstream frame = closest overall | downstream
+only}, exactly this one reproduces ``nearby.shape == (7074, 12)``, the locus filter ``(4, 23)`` and the guide table
+``(900, 23)`` -- the exact search yields 899 rows, one fewer, which is the one direction an exact search can differ from
+the reference's approximate HNSW search (a guide the HNSW search kept because it missed a neighbour at distance 1).
+Hand-computed interval fixtures and a brute-force cross-check are in tests/test_annotation.py.
 
 Feature ids: the reference hashes Biopython's ``str(SeqFeature)`` (core.py:721) or pybedtools' ``str(Interval)``
 (core.py:739).  The GFF form (the tab-joined line) is reproduced exactly; the GenBank form follows Biopython's
@@ -266,8 +278,8 @@ class Annotation:
 
     # ---- nearest-feature join ---------------------------------------------------------------------------------------------
     def _get_nearby_features(self) -> None:
-        """Closest feature of every guide, once over all features ("downstream" frame: ties prefer the downstream one)
-        and once ignoring downstream features ("upstream" frame) -- core.py:815-848."""
+        """First feature downstream of every guide ("downstream" frame) and the overlapping-or-nearest-upstream feature
+        ("upstream" frame), core.py:815-848; see the module docstring for the bedtools semantics restated here."""
         feat = self.genbank_bed_df
         tb = self.target_bed_df
         f_chrom = feat["chrom"].astype(str).to_numpy()
@@ -293,10 +305,10 @@ class Annotation:
             fsel = np.flatnonzero(f_chrom == chrom)
             if len(fsel) == 0:
                 continue
-            for ignore_down in (False, True):
-                fi, d = closest_features(g_start[gsel], g_end[gsel], g_strand[gsel] == "-", f_start[fsel], f_end[fsel], ignore_down)
-                res[ignore_down][0][gsel] = np.where(fi >= 0, fsel[np.maximum(fi, 0)], -1)
-                res[ignore_down][1][gsel] = d
+            for upstream_frame in (False, True):
+                fi, d = closest_features(g_start[gsel], g_end[gsel], f_start[fsel], f_end[fsel], upstream_frame)
+                res[upstream_frame][0][gsel] = np.where(fi >= 0, fsel[np.maximum(fi, 0)], -1)
+                res[upstream_frame][1][gsel] = d
 
         def frame(fi, d, direction):
             has = fi >= 0
@@ -385,55 +397,37 @@ class Annotation:
 
 
 # ---- bedtools closest, restated on sorted arrays -------------------------------------------------------------------------
-def closest_features(g_start, g_end, g_minus, f_start, f_end, ignore_downstream: bool):
-    """For every guide interval [g_start, g_end) on one contig: index of the closest feature [f_start, f_end) (features
-    sorted by start; -1 if none is eligible) and the ``-D a`` signed distance.
+def closest_features(g_start, g_end, f_start, f_end, upstream_frame: bool):
+    """For every guide interval [g_start, g_end) on one contig: index of the reported feature [f_start, f_end) (features
+    sorted by start; -1 if none is eligible) and the signed distance, for one of the reference's two frames.
 
-    Overlap -> 0.  Otherwise the nearest feature on the left (largest end <= guide start) and on the right (smallest
-    start >= guide end) compete with distances gap + 1; equal distances: the DOWNSTREAM one wins (``-fd``), downstream
-    being the right side for '+' guides and the left side for '-' guides.  ``ignore_downstream`` (``-id``) removes the
-    downstream side from the competition.  Among several features at the same distance on one side the first in sorted
-    order is taken (``-t first``).  A feature upstream of the guide is reported with a negative distance."""
+    downstream frame (``-fd``): the feature with the smallest start >= guide end (equal starts: first in sorted order);
+        distance = start - guide end + 1 (book-ended intervals are 1 apart).
+    upstream frame (``-id``): the first feature in sorted order that overlaps the guide (distance 0), else the feature
+        with the largest end <= guide start (equal ends: first in sorted order); distance = -(guide start - end + 1)."""
     g_start, g_end = np.asarray(g_start, np.int64), np.asarray(g_end, np.int64)
-    g_minus = np.asarray(g_minus, bool)
     f_start, f_end = np.asarray(f_start, np.int64), np.asarray(f_end, np.int64)
     n, m = len(g_start), len(f_start)
-    idx = np.full(n, -1, np.int64)
-    dist = np.full(n, -1, np.int64)
     if m == 0 or n == 0:
-        return idx, dist
-    # overlap: first feature (in start order) with end > guide start, provided its start < guide end
+        return np.full(n, -1, np.int64), np.full(n, -1, np.int64)
+    if not upstream_frame:
+        ri = np.searchsorted(f_start, g_end, side="left")
+        has = ri < m
+        j = np.minimum(ri, m - 1)
+        return np.where(has, j, -1), np.where(has, f_start[j] - g_end + 1, -1)
+    # overlap: the first feature (in start order) whose end lies behind the guide start, provided it starts before
+    # the guide ends.  pmax[i] > g_start says SOME feature j <= i ends behind g_start; the first such i is that feature.
     pmax = np.maximum.accumulate(f_end)
-    first_open = np.searchsorted(pmax, g_start, side="right")           # first i with prefix-max end > g_start
+    first_open = np.searchsorted(pmax, g_start, side="right")
     n_start_lt = np.searchsorted(f_start, g_end, side="left")           # features with start < g_end
-    # pmax[i] > g_start says SOME feature j <= i ends behind g_start; the first such i is itself that feature
     overlap = first_open < n_start_lt
-    # left neighbour: largest end <= g_start; ties on end -> first in start order
     e_order = np.lexsort((-np.arange(m), f_end))                         # by end; equal ends: later file position first
     e_sorted = f_end[e_order]
-    li = np.searchsorted(e_sorted, g_start, side="right") - 1
+    li = np.searchsorted(e_sorted, g_start, side="right") - 1            # largest end <= g_start, first in file order
     has_l = li >= 0
-    left = np.where(has_l, e_order[np.maximum(li, 0)], -1)
-    dl = np.where(has_l, g_start - f_end[np.maximum(left, 0)] + 1, np.iinfo(np.int64).max)
-    # right neighbour: smallest start >= g_end; ties on start -> first in start order (searchsorted 'left')
-    ri = np.searchsorted(f_start, g_end, side="left")
-    has_r = ri < m
-    right = np.where(has_r, np.minimum(ri, m - 1), -1)
-    dr = np.where(has_r, f_start[np.minimum(ri, m - 1)] - g_end + 1, np.iinfo(np.int64).max)
-    # which side is downstream of the guide: right for '+', left for '-'
-    down_is_right = ~g_minus
-    if ignore_downstream:
-        has_r = has_r & ~down_is_right
-        has_l = has_l & down_is_right
-        dl = np.where(has_l, dl, np.iinfo(np.int64).max)
-        dr = np.where(has_r, dr, np.iinfo(np.int64).max)
-    pick_right = (dr < dl) | ((dr == dl) & down_is_right)
-    side_idx = np.where(pick_right, right, left)
-    side_d = np.where(pick_right, dr, dl)
-    side_ok = np.where(pick_right, has_r, has_l)
-    upstream = np.where(pick_right, ~down_is_right, down_is_right)       # the picked side is the guide's upstream side
-    idx = np.where(overlap, first_open, np.where(side_ok, side_idx, -1))
-    dist = np.where(overlap, 0, np.where(side_ok, np.where(upstream, -side_d, side_d), -1))
+    left = e_order[np.maximum(li, 0)]
+    idx = np.where(overlap, np.minimum(first_open, m - 1), np.where(has_l, left, -1))
+    dist = np.where(overlap, 0, np.where(has_l, -(g_start - f_end[left] + 1), -1))
     return idx, dist
 
 

@@ -1,14 +1,14 @@
-"""Thin runner of the off-target hot path with the reference CLI's flags (guidemaker/cli.py:22-76).
+"""Runner of the off-target hot path and the annotation join with the reference CLI's flags (guidemaker/cli.py:22-76).
 
-It runs the reference's workflow (cli.py:161-189, :230-245) up to the point where the annotation join starts:
-PAM scan -> restriction flag -> seed uniqueness -> exact kNN -> BED frame, and the random controls.  It writes
+It follows the reference's workflow (cli.py:161-245): PAM scan -> restriction flag -> seed uniqueness -> exact kNN -> BED
+frame -> nearest-feature join -> filters -> guide table (-> CFD scores) -> random controls, and writes
 
   rawguides.csv.gz   the reference's --raw_output_only table (header Chromosome,Start,Stop,gRNA,Strand; cli.py:191)
-  offtargets.csv.gz  one row per kept guide locus: position, PAM, and the k nearest guides with their distances
+  targets.csv.gz     the guide table (cli.py:226-227) when annotation is available (--genbank or --gff)
+  offtargets.csv.gz  one row per kept guide locus with its k nearest guides (always written; not in the reference)
   controls.csv.gz    the reference's control table (written with its index column, cli.py:239)
 
-The feature-annotation join (bedtools), Doench / CFD scoring and plots are outside this repo's scope;
-`targets.csv.gz` needs them and is therefore not produced here."""
+Doench efficiency scoring (an ONNX model) and the plots are outside this repo's scope."""
 from __future__ import annotations
 
 import argparse
@@ -31,7 +31,7 @@ def myparser():
     p = argparse.ArgumentParser(description="guidemaker_b200: GuideMaker's off-target hot path on a B200")
     p.add_argument('--genbank', '-i', nargs='+', type=str, required=False)
     p.add_argument('--fasta', '-f', nargs='+', type=str, required=False)
-    p.add_argument('--gff', '-g', nargs='+', type=str, required=False, help="accepted for compatibility; annotation is out of scope")
+    p.add_argument('--gff', '-g', nargs='+', type=str, required=False, help="GFF/GTF annotation (with --fasta)")
     p.add_argument('--pamseq', '-p', type=str, required=True)
     p.add_argument('--outdir', '-o', type=str, required=True)
     p.add_argument('--raw_output_only', action='store_true')
@@ -40,6 +40,11 @@ def myparser():
     p.add_argument('--lsr', type=int, default=10, choices=range(0, 28, 1), metavar="[0-27]")
     p.add_argument('--dtype', type=str, choices=['hamming', 'leven'], default='hamming')
     p.add_argument('--dist', type=int, choices=range(0, 6, 1), metavar="[0-5]", default=2)
+    p.add_argument('--before', type=int, default=100, choices=range(1, 501, 1), metavar="[1-500]")
+    p.add_argument('--into', type=int, default=200, choices=range(1, 501, 1), metavar="[1-500]")
+    p.add_argument('--attribute_key', type=str, default=None)
+    p.add_argument('--filter_by_attribute', nargs="*", default=[])
+    p.add_argument('--cfd_score', action='store_true')
     p.add_argument('--knum', type=int, default=5, choices=range(2, 21, 1), metavar="[2-20]")
     p.add_argument('--controls', type=int, default=1000, choices=range(0, 100001, 1), metavar="[0-100000]")
     p.add_argument('--threads', type=int, default=2, help="accepted and ignored (the search runs on the GPU)")
@@ -85,8 +90,31 @@ def main(arglist: list = None):
         tf_df = tl.export_bed()
         os.makedirs(args.outdir, exist_ok=True)
         tf_df.to_csv(os.path.join(args.outdir, "rawguides.csv.gz"), index=False, header=["Chromosome", "Start", "Stop", "gRNA", "Strand"])
+        n_guides = len(tl.neighbors)
         if not args.raw_output_only:
             offtarget_table(tl).to_csv(os.path.join(args.outdir, "offtargets.csv.gz"), index=False)
+            if args.genbank or args.gff:
+                logger.info("Create GuideMaker Annotation object")
+                anno = core.Annotation(annotation_list=args.genbank or args.gff, annotation_type="genbank" if args.genbank else "gff",
+                                       target_bed_df=tf_df)
+                logger.info("Identify genomic features")
+                anno.get_annotation_features()
+                logger.info("Total number of %s in the input genome: %d" % anno.locuslen())
+                logger.info("Find genomic features closest the guides")
+                anno._get_nearby_features()
+                logger.info("Select guides that start between +%s and -%s of a feature start" % (args.before, args.into))
+                anno._filter_features(before_feat=args.before, after_feat=args.into)
+                logger.info("Select description columns")
+                anno._get_qualifiers(configpath=args.config)
+                logger.info("Format the output")
+                anno._format_guide_table(tl)
+                prettydf = anno._filterlocus(args.attribute_key, args.filter_by_attribute)
+                if args.cfd_score:
+                    logger.info("Calculating CFD score for assessing off-target activity of gRNAs")
+                    prettydf = core.cfd_score(df=prettydf)
+                logger.info("Number of Guides within a gene coordinates i.e. zero Feature distance: %d", prettydf['Feature distance'].isin([0]).sum())
+                prettydf.to_csv(os.path.join(args.outdir, "targets.csv.gz"), index=False)
+                n_guides = len(prettydf)
             if args.controls > 0:
                 logger.info("Creating random control guides")
                 cmin, cmed, randomdf = tl.get_control_seqs(records, configpath=args.config, length=args.guidelength,
@@ -101,7 +129,7 @@ def main(arglist: list = None):
         logger.info("PAM orientation: %s", args.pam_orientation)
         logger.info("Genome strand(s) searched: %s", "both")
         logger.info("Total PAM sites considered: %d", lengthoftl)
-        logger.info("Guide RNA candidates found: %d", len(tl.neighbors))
+        logger.info("Guide RNA candidates found: %d", n_guides)
     except Exception:
         logger.exception("guidemaker_b200 terminated with errors. See the log file for details.")
         raise SystemExit(1)
@@ -110,20 +138,14 @@ def main(arglist: list = None):
 def offtarget_table(tl: "core.TargetProcessor") -> pd.DataFrame:
     """One row per locus whose guide survived both filters (first-seen seed, nearest other guide >= dist), with the
     columns of the reference's final table that come from the hot path (core.py:917-942): guide, position, strand,
-    PAM, `Similar guides` and `Similar guide distances` (';'-joined).  Vectorised over the neighbour arrays."""
+    PAM, `Similar guides` and `Similar guide distances` (';'-joined).  Assembled from the neighbour arrays, no per-row Python."""
+    from .annotation import neighbor_positions, similar_guide_strings
     nb = tl.neighbors
     t = tl.targets.loc[tl.targets['isseedduplicated'] == False]  # noqa: E712
-    keys = pd.Index(np.char.decode(nb.key_array(), "ascii"))
-    pos = keys.get_indexer(t['target'])
+    pos = neighbor_positions(nb, t['target'].astype(str).to_numpy())
     t = t.loc[pos >= 0]
     pos = pos[pos >= 0]
-    idx, dist = nb.index_matrix()[pos], nb.distance_matrix()[pos]
-    from ._encode import decode_guides
-    uniq = np.char.decode(decode_guides(nb.uniq, nb.L), "ascii")
-    valid = idx >= 0
-    seqs = np.where(valid, uniq[np.where(valid, idx, 0)], "")
-    sim = [";".join(r[v]) for r, v in zip(seqs, valid)]
-    dd = [";".join(str(int(x)) for x in r[v]) for r, v in zip(dist, valid)]
+    dd, sim = similar_guide_strings(nb, pos)
     return pd.DataFrame({"Guide sequence": t['target'].to_numpy(), "Accession": t['seqid'].astype(str).to_numpy(),
                          "Guide start": t['start'].to_numpy() + 1, "Guide end": t['stop'].to_numpy(),
                          "Guide strand": np.where(t['strand'].to_numpy(dtype=bool), '+', '-'), "PAM": t['exact_pam'].astype(str).to_numpy(),

@@ -533,3 +533,9 @@ def extend_ambiguous_dna(seq: str) -> List[str]:
         "K": "GT", "V": "ACG", "H": "ACT", "D": "AGT", "B": "CGT", "X": "GATC", "N": "GATC",
     }
     return ["".join(i) for i in product(*[ambiguous_dna_values[j] for j in seq])]
+
+
+# the rest of guidemaker.core's public surface lives in sibling modules; re-exported here so that
+# ``guidemaker_b200.core.Annotation`` / ``.cfd_score`` resolve as they do in the reference (core.py:636, :1129)
+from .annotation import Annotation  # noqa: E402,F401
+from .cfd import cfd_score  # noqa: E402,F401

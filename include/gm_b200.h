@@ -141,6 +141,13 @@ int gm_restriction_scan(const uint64_t *guide2bit, int64_t n, int L, const uint8
 int gm_restriction_scan_dev(const uint64_t *d_guide2bit, int64_t n, int L, const uint8_t *motif_sets,
                             const int32_t *motif_len, int n_motifs, uint8_t *d_has_site, void *stream);
 
+/* ---- CFD off-target score (core.py:1129-1148, cfd_score_calculator.py:62-85) ------------------------------------------
+ * out[i*k + j] = product, over the last 20 positions p where guide i and off-target (i, j) differ, of
+ * mm_table[rna base of the guide][dna base = complement of the off-target base][pos - 1]; mm_table is 4 x 4 x 20 doubles
+ * (A,C,G,U x A,C,G,T x position 1..20).  Double precision, positions in ascending order: equal to the reference's
+ * Python float.  wt2bit: n guides, off2bit: n*k off-targets (row-major), both guide2bit of length L. */
+int gm_cfd_scores(const uint64_t *wt2bit, const uint64_t *off2bit, int64_t n, int k, int L, const double *mm_table, double *out);
+
 /* ---- K3/K4/K5: exact brute-force kNN index -----------------------------------------------------
  * The index is the table of distinct guides resident in HBM (bit-plane layout).
  * n_u < 2^27. */

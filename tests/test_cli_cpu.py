@@ -56,3 +56,22 @@ def test_cli_raw_output_and_offtargets(oracle_engine, tmp_path, carsonella_ref):
     cli.main(["--fasta", os.path.join(GOLDEN, "carsonella.fa.gz"), "--pamseq", "NGG", "--outdir", str(tmp_path / "raw"), "--raw_output_only",
               "--controls", "0", "--log", str(tmp_path / "log.txt")])
     assert os.listdir(tmp_path / "raw") == ["rawguides.csv.gz"]
+
+
+def test_cli_targets_table_from_genbank(oracle_engine, tmp_path):
+    """--genbank: the guide table targets.csv.gz (cli.py:195-227) with the reference's 23 columns and 1-based starts"""
+    out = tmp_path / "out"
+    cli.main(["--genbank", os.path.join(GOLDEN, "carsonella.gbk.gz"), "--pamseq", "NGG", "--outdir", str(out), "--pam_orientation", "5prime",
+              "--guidelength", "20", "--lsr", "10", "--dist", "2", "--knum", "10", "--controls", "0", "--log", str(tmp_path / "log.txt"),
+              "--restriction_enzyme_list", "NRAGCA"])
+    t = pd.read_csv(out / "targets.csv.gz")
+    assert t.shape == (899, 23)                      # reference: (900, 23) with its approximate search (tests/test_core.py:222)
+    assert list(t.columns[:9]) == ['Guide name', 'Guide sequence', 'GC', 'dtype', 'Accession', 'Guide start', 'Guide end', 'Guide strand', 'PAM']
+    assert {"locus_tag", "product", "protein_id"} <= set(t.columns)
+    assert (t["Guide end"] - t["Guide start"] + 1 == 20).all() and (t["Accession"] == "AP009180.1").all()
+    assert t["Feature start"].is_monotonic_increasing
+    out2 = tmp_path / "out2"
+    cli.main(["--genbank", os.path.join(GOLDEN, "carsonella.gbk.gz"), "--pamseq", "NGG", "--outdir", str(out2), "--pam_orientation", "5prime",
+              "--knum", "10", "--controls", "0", "--log", str(tmp_path / "log.txt"), "--restriction_enzyme_list", "NRAGCA",
+              "--attribute_key", "locus_tag", "--filter_by_attribute", "CRP_001"])
+    assert pd.read_csv(out2 / "targets.csv.gz").shape == (4, 23)                      # tests/test_core.py:246
