@@ -157,9 +157,14 @@ class PamTarget:
         ids, seqs, raw = [], [], []
         for record in seq_record_iter:
             ids.append(record.id)
-            s = str(record.seq)
-            seqs.append(s)
-            raw.append(s.encode("latin-1", "replace"))
+            seq = record.seq
+            if isinstance(getattr(seq, "_raw", None), bytes):      # fastaio records already hold ASCII bytes
+                seqs.append(seq)                                   # (str() of it only if a row needs literal slicing)
+                raw.append(seq._raw)
+            else:
+                s = str(seq)
+                seqs.append(s)
+                raw.append(s.encode("latin-1", "replace"))
         # one launch over the whole genome: records joined by an invalid base, which can neither
         # match a PAM position nor sit inside a target, so no hit straddles two records
         lens = np.array([len(b) for b in raw], dtype=np.int64)
@@ -250,7 +255,7 @@ class PamTarget:
             # match start/end on the forward text, from the target window
             ms = (st - P if fwd else st + L) if five else (st + L if fwd else st - P)
             a = ms - 3 if fwd == five else ms + P - 27       # 5p fwd / 3p rev slice [ms-3, ms+27); others [me-27, me+3)
-            piece = seqs[rec[i]][a: a + 30]
+            piece = str(seqs[rec[i]])[a: a + 30]
             piece = (piece if fwd else _reverse_complement(piece)).encode("latin-1", "replace")
             width[i] = len(piece)
             parts.append(flat[prev * 30: i * 30])     # the untouched rows before this one, as a view

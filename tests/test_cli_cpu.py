@@ -75,3 +75,26 @@ def test_cli_targets_table_from_genbank(oracle_engine, tmp_path):
               "--knum", "10", "--controls", "0", "--log", str(tmp_path / "log.txt"), "--restriction_enzyme_list", "NRAGCA",
               "--attribute_key", "locus_tag", "--filter_by_attribute", "CRP_001"])
     assert pd.read_csv(out2 / "targets.csv.gz").shape == (4, 23)                      # tests/test_core.py:246
+
+
+def test_bulk_readers_edge_cases(tmp_path):
+    """the bulk byte-level readers give what a line-by-line reader (and Biopython's upper-cased records) would"""
+    fa = tmp_path / "x.fa"
+    fa.write_bytes(b"; junk before the first header\n>r1 desc\r\nacgt nn\r\n\r\nACGT\r\n>r2\n>r3 empty above\nGG>A\n")
+    recs = fastaio.get_records([str(fa)], "fasta")
+    assert [(r.id, str(r.seq)) for r in recs] == [("r1", "ACGTNNACGT"), ("r2", ""), ("r3", "GG>A")]
+    assert len(recs[0]) == 10 and recs[0].seq == "ACGTNNACGT" and recs[0].seq[2:5] == "GTN"
+    gz = tmp_path / "x.fa.gz"
+    gz.write_bytes(gzip.compress(fa.read_bytes()))
+    assert [(r.id, str(r.seq)) for r in fastaio.get_records([str(gz)], "fasta")] == [(r.id, str(r.seq)) for r in recs]
+    gb = tmp_path / "two.gbk"
+    _write_genbank(gb, "AB000001.1", "ACGTACGTAC" * 13 + "GGG")
+    first = gb.read_text()
+    _write_genbank(gb, "AB000002.2", "TTTTGGGGCCCCAAAA")
+    gb.write_text(first + gb.read_text())
+    recs = fastaio.get_records([str(gb)], "genbank")
+    assert [(r.id, len(r)) for r in recs] == [("AB000001.1", 133), ("AB000002.2", 16)]
+    assert str(recs[0].seq) == "ACGTACGTAC" * 13 + "GGG" and str(recs[1].seq) == "TTTTGGGGCCCCAAAA"
+    empty = tmp_path / "none.fa"
+    empty.write_text("no header here\n")
+    assert fastaio.get_records([str(empty)], "fasta") == []
