@@ -30,6 +30,7 @@ _LIB = None
 _SIGS = {
     "gm_init": [ctypes.c_int],
     "gm_version": [],
+    "gm_trim": [],
     "gm_device_info": [ctypes.POINTER(ctypes.c_int)] * 3 + [_c_i64p],
     "gm_scan_create": [_vp, ctypes.c_int64, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                        ctypes.POINTER(_vp), _c_i64p, _c_i64p],

@@ -3,7 +3,9 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <chrono>
+#include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -45,6 +47,74 @@ double now_ms() {
 void trace(const char *what, double t0_ms) {
     if (trace_on()) fprintf(stderr, "[gm_trace] %-28s %9.3f ms\n", what, now_ms() - t0_ms);
 }
+// ---- caching device allocator -------------------------------------------------------------------------------------------
+struct DevBlock { void *p; size_t bytes; cudaEvent_t ev; cudaStream_t st; };
+static std::mutex g_mem_mu;
+static std::vector<DevBlock> g_mem_free;
+static std::unordered_map<void *, DevBlock> g_mem_live;
+
+static size_t round_bytes(size_t b) {
+    if (b < 512) b = 512;
+    const size_t g = b >= (1u << 20) ? (size_t)2 << 20 : 512;            // 2 MB steps for large blocks, 512 B for small ones
+    return (b + g - 1) / g * g;
+}
+
+static void mem_trim_locked() {
+    for (auto &b : g_mem_free) { cudaEventSynchronize(b.ev); cudaEventDestroy(b.ev); cudaFree(b.p); }
+    g_mem_free.clear();
+}
+
+cudaError_t dev_alloc(void **p, size_t bytes, cudaStream_t st) {
+    bytes = round_bytes(bytes);
+    {
+        std::lock_guard<std::mutex> lk(g_mem_mu);
+        int best = -1;
+        const size_t limit = bytes + (bytes >> 1) + ((size_t)4 << 20);   // do not burn a much larger block on a small request
+        for (int i = 0; i < (int)g_mem_free.size(); i++)
+            if (g_mem_free[i].bytes >= bytes && g_mem_free[i].bytes <= limit && (best < 0 || g_mem_free[i].bytes < g_mem_free[best].bytes)) best = i;
+        if (best >= 0) {
+            DevBlock b = g_mem_free[best];
+            g_mem_free.erase(g_mem_free.begin() + best);
+            if (b.st != st) {                                            // released on another stream: order behind that release
+                cudaError_t e = cudaStreamWaitEvent(st, b.ev, 0);
+                if (e != cudaSuccess) { g_mem_free.push_back(b); return e; }
+            }
+            b.st = st;
+            g_mem_live[b.p] = b;
+            *p = b.p;
+            return cudaSuccess;
+        }
+    }
+    DevBlock b;
+    b.bytes = bytes;
+    b.st = st;
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e == cudaErrorMemoryAllocation) {                                // give the cached blocks back and try once more
+        cudaGetLastError();
+        { std::lock_guard<std::mutex> lk(g_mem_mu); mem_trim_locked(); }
+        e = cudaMalloc(&b.p, bytes);
+    }
+    if (e != cudaSuccess) return e;
+    e = cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) { cudaFree(b.p); return e; }
+    std::lock_guard<std::mutex> lk(g_mem_mu);
+    g_mem_live[b.p] = b;
+    *p = b.p;
+    return cudaSuccess;
+}
+
+void dev_free(void *p, cudaStream_t st) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_mem_mu);
+    auto it = g_mem_live.find(p);
+    if (it == g_mem_live.end()) { cudaFree(p); return; }                 // not ours (should not happen)
+    DevBlock b = it->second;
+    g_mem_live.erase(it);
+    b.st = st;
+    cudaEventRecord(b.ev, st);                                           // the block is reusable once the work queued so far is done
+    g_mem_free.push_back(b);
+}
+
 void prefault(void *p, size_t bytes) {
     if (!p || bytes < (8u << 20)) return;
     unsigned nt = std::thread::hardware_concurrency();
@@ -100,17 +170,17 @@ extern "C" int gm_init(int device) {
     }
     GM_CUDA(cudaSetDevice(device));
     GM_CUDA(cudaFree(0));
-    {   // keep freed blocks in the stream-ordered pool (no unmap between calls)
-        cudaMemPool_t pool;
-        GM_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-        unsigned long long keep = ~0ULL;
-        GM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    }
     g_device = device;
     g_sm_count = p.multiProcessorCount;
     g_cc_major = p.major;
     g_cc_minor = p.minor;
     g_mem = (long long)p.totalGlobalMem;
+    return GM_OK;
+}
+
+extern "C" int gm_trim(void) {
+    std::lock_guard<std::mutex> lk(g_mem_mu);
+    mem_trim_locked();
     return GM_OK;
 }
 

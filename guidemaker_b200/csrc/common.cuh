@@ -42,10 +42,13 @@ int device_sm_count();
 bool initialised();
 int ensure_init();
 
-// Device memory comes from the stream-ordered allocator; gm_init raises the pool's release threshold
-// so freed blocks stay mapped and the next call's allocations cost microseconds, not a map/unmap.
-inline cudaError_t dev_alloc(void **p, size_t bytes, cudaStream_t st) { return cudaMallocAsync(p, bytes ? bytes : 16, st); }
-inline void dev_free(void *p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
+// Device scratch memory comes from a small caching allocator (api.cu): cudaMalloc'd blocks are kept on a free list and
+// handed out again, stream-ordered -- a block records an event on the stream it was released on, and a taker on another
+// stream waits for that event first.  In the steady state no driver allocation call is made at all.  (The driver's own
+// stream-ordered pool, cudaMallocAsync, was used first: on the B200 boxes it stalled sporadically for 50-2000 ms inside
+// an allocation when buffers of a few hundred MB were returned and taken again every call -- tools/e2e_stall_probe.py.)
+cudaError_t dev_alloc(void **p, size_t bytes, cudaStream_t st);
+void dev_free(void *p, cudaStream_t st);
 
 // Touch every page of a host OUTPUT buffer with several threads before a large device->host copy lands in it.  A fresh
 // numpy array is untouched virtual memory: the copy's destination pages are then faulted in (and zero-filled by the

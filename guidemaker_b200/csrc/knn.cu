@@ -27,6 +27,7 @@
 //
 // Merge kernel: k smallest keys over the splits of a query -> (int32 idx, uint8 dist) rows.
 #include "knn_common.cuh"
+#include <mutex>
 #include <new>
 #include <stdlib.h>
 
@@ -273,14 +274,38 @@ __global__ void knn_merge_kernel(const uint32_t *__restrict__ lists, int splits,
 
 // ---- host side ------------------------------------------------------------------------------------------
 
+// One retired workspace is kept for the next index (callers that rebuild the index for every batch -- bench e2e, the
+// control rounds -- would otherwise return ~0.4 GB to the pool and take it back on every call).  gm_index_free parks
+// it here after a device synchronise, so whoever adopts it next needs no stream ordering.
+static std::mutex g_spare_mu;
+static void *g_spare_ws = nullptr;
+static size_t g_spare_bytes = 0;
+
+static void park_ws(void *ws, size_t bytes) {
+    if (!ws) return;
+    std::lock_guard<std::mutex> lk(g_spare_mu);
+    if (bytes > g_spare_bytes) { dev_free(g_spare_ws, 0); g_spare_ws = ws; g_spare_bytes = bytes; }
+    else dev_free(ws, 0);
+}
+
 static int ensure_ws(Index *ix, size_t bytes, cudaStream_t st) {
     if (bytes <= ix->ws_bytes) return GM_OK;
+    const double t0 = now_ms();
     dev_free(ix->ws, st);                      // stream ordered: earlier kernels on `st` finish first
     ix->ws = nullptr;
     ix->ws_bytes = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_spare_mu);
+        if (g_spare_ws && g_spare_bytes >= bytes) {
+            ix->ws = g_spare_ws; ix->ws_bytes = g_spare_bytes;
+            g_spare_ws = nullptr; g_spare_bytes = 0;
+            return GM_OK;
+        }
+    }
     bytes = (bytes + (bytes >> 3) + 4095) & ~(size_t)4095;
     GM_CUDA(dev_alloc(&ix->ws, bytes, st));
     ix->ws_bytes = bytes;
+    trace("  knn: workspace alloc", t0);
     return GM_OK;
 }
 
@@ -368,9 +393,11 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     uint32_t *tlists = reinterpret_cast<uint32_t *>((char *)ix->ws + qp_bytes + main_bytes);
     uint32_t *wlists = warm ? reinterpret_cast<uint32_t *>((char *)ix->ws + qp_bytes + list_bytes) : nullptr;
 
+    double t_l = now_ms();
     to_planes_kernel<<<(unsigned)((q_pad + 255) / 256), 256, 0, st>>>(d_q, q, q_pad, qplanes);
     count_launch();
     GM_CUDA(cudaMemsetAsync(lists, 0xFF, list_bytes + warm_bytes, st));
+    trace("  knn: to_planes + memset enqueue", t_l);
 
     ScanArgs a;
     a.tplanes = ix->planes;
@@ -442,6 +469,7 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     pairs += (double)q * ((double)ix->n_u - (double)first_chunk * CHUNK);
     prof_end(slot, st, pairs);
 
+    trace("  knn: scan launches enqueue", t_l);
     knn_merge_kernel<<<(unsigned)((q + 127) / 128), 128, 0, st>>>(lists, splits, q, q_pad, k, tlists, tail_splits, tail_q0, tail_q, d_idx, d_dist,
                                                                   dist_only);
     count_launch();
@@ -537,7 +565,7 @@ extern "C" int gm_index_free(void *index) {
     cudaDeviceSynchronize();
     dev_free(ix->planes, 0);
     dev_free(ix->planes_perm, 0);
-    dev_free(ix->ws, 0);
+    park_ws(ix->ws, ix->ws_bytes);
     delete ix;
     return GM_OK;
 }

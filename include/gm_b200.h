@@ -66,6 +66,9 @@ const char *gm_last_error(void);
 int         gm_version(void);
 /* sm_count, compute capability and total HBM of the device chosen by gm_init */
 int         gm_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *mem_bytes);
+/* The library keeps released device scratch blocks for reuse (no driver allocation in the steady state); gm_trim returns
+ * the cached blocks to the driver (handles stay valid). */
+int         gm_trim(void);
 
 /* ---- K1: IUPAC PAM scan over both strands ------------------------------------------------------
  * seq_ascii: n bytes of one record (or several records joined by any non-ACGT byte).  Only
