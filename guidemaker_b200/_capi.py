@@ -64,11 +64,16 @@ _SIGS = {
     "gm_knn_dev": [_vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp],
     "gm_min_dist": [_vp, _vp, ctypes.c_int64, _vp],
     "gm_min_dist_dev": [_vp, _vp, ctypes.c_int64, _vp, _vp],
+    "gm_comm_unique_id": [_vp],
+    "gm_comm_create": [_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)],
+    "gm_comm_free": [_vp],
+    "gm_knn_sharded": [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp],
     "gm_prof_enable": [ctypes.c_int],
     "gm_prof_reset": [],
     "gm_prof_read": [ctypes.POINTER(ctypes.c_double), _c_i64p, ctypes.POINTER(ctypes.c_double), _c_i64p],
     "gm_knn_tune": [ctypes.c_int, ctypes.c_int, ctypes.c_int],
     "gm_knn_engine": [ctypes.c_int],
+    "gm_index_tune": [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int],
     "gm_microbench": [ctypes.c_int, ctypes.POINTER(ctypes.c_double)],
 }
 EXPORTS = tuple(_SIGS) + ("gm_last_error",)
@@ -335,6 +340,10 @@ class Index:
     def min_dist_dev(self, d_q: int, q: int, d_dist: int, stream: int = 0) -> None:
         _check(load_library().gm_min_dist_dev(self._h, _vp(d_q), int(q), _vp(d_dist), _vp(stream)), "gm_min_dist_dev")
 
+    def tune(self, engine: int = -1, queries_per_thread: int = -1, splits: int = -1, warm_sample: int = -2) -> None:
+        """per-handle engine / tuning (defaults follow knn_engine / knn_tune)"""
+        _check(load_library().gm_index_tune(self._h, int(engine), int(queries_per_thread), int(splits), int(warm_sample)), "gm_index_tune")
+
     def close(self):
         if self._h:
             load_library().gm_index_free(self._h)
@@ -345,6 +354,38 @@ class Index:
             self.close()
         except Exception:
             pass
+
+
+# ---- multi-GPU through the C ABI (NCCL inside the library) ---------------------------------------------
+class Comm:
+    """NCCL communicator owned by the library: rank 0 calls ``Comm.unique_id()``, the host carries the 128 bytes to the
+    other ranks, every rank constructs ``Comm(id, rank, world)``."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = np.zeros(128, np.uint8)
+        _check(load_library().gm_comm_unique_id(_p(buf)), "gm_comm_unique_id")
+        return buf.tobytes()
+
+    def __init__(self, unique_id: bytes, rank: int, world: int):
+        init()
+        self._h = _vp()
+        self.rank, self.world = int(rank), int(world)
+        buf = np.frombuffer(unique_id, np.uint8).copy()
+        _check(load_library().gm_comm_create(_p(buf), self.rank, self.world, ctypes.byref(self._h)), "gm_comm_create")
+
+    def knn(self, index: "Index", q2bit: np.ndarray, k: int):
+        """gm_knn_sharded: every rank passes the same rows; every rank gets all rows back"""
+        q2bit = np.ascontiguousarray(q2bit, np.uint64)
+        idx = np.empty((len(q2bit), k), np.int32); dist = np.empty((len(q2bit), k), np.uint8)
+        _check(load_library().gm_knn_sharded(index._h, self._h, _p(q2bit) if len(q2bit) else None, len(q2bit), int(k), _p(idx), _p(dist)),
+               "gm_knn_sharded")
+        return idx, dist
+
+    def close(self):
+        if self._h:
+            load_library().gm_comm_free(self._h)
+            self._h = _vp()
 
 
 # ---- measurement hooks ------------------------------------------------------------------------------

@@ -325,15 +325,18 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     GM_ARG(d_q && d_dist && (dist_only || d_idx), "gm_knn: NULL buffer");
 
     // queries per thread: Levenshtein keeps 2 more state words per pair, so it uses R=4
-    const int R = ix->metric == GM_METRIC_HAMMING ? (g_tune_r == 4 ? 4 : 8) : (g_tune_r == 4 ? 4 : 8);
-    const bool use_tc = g_tune_engine == 1 && ix->metric == GM_METRIC_HAMMING;
+    const int tune_r = ix->tune_r > 0 ? ix->tune_r : g_tune_r;
+    const int tune_splits = ix->tune_splits >= 0 ? ix->tune_splits : g_tune_splits;
+    const int tune_warm = ix->tune_warm >= -1 ? ix->tune_warm : g_tune_warm;
+    const int R = tune_r == 4 ? 4 : 8;
+    const bool use_tc = (ix->engine >= 0 ? ix->engine : g_tune_engine) == 1 && ix->metric == GM_METRIC_HAMMING;
     const int QT = THREADS * R;
     const int64_t tiles = (q + QT - 1) / QT;
     const int64_t q_pad = tiles * QT;
     const int n_chunks = (int)(ix->n_pad / CHUNK);
 
     // target splits: enough CTAs for >= ~16 per SM so the last wave is a small fraction
-    int splits = g_tune_splits;
+    int splits = tune_splits;
     // K3b runs one CTA per SM, so a launch of T query tiles takes ceil(T / SMs) waves and the last one may be nearly
     // empty (T = 335 on each of 8 GPUs for the 6.3 Mb config: 2.26 waves of work in 3).  Two-tier launch: the largest
     // multiple of the SM count runs unsplit, the remaining `tail_tiles` are cut into `tail_splits` target ranges so they
@@ -358,7 +361,7 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
         splits = (int)((want + grid_x - 1) / grid_x);
     }
     // warm start: worthwhile only when the table is much larger than the sample
-    int warm = g_tune_warm < 0 ? (use_tc ? 8 : 4) * CHUNK : g_tune_warm;   // measured: 8192 is best for K3b, 4096 for K3a
+    int warm = tune_warm < 0 ? (use_tc ? 8 : 4) * CHUNK : tune_warm;   // measured: 8192 is best for K3b, 4096 for K3a
     warm = (warm + CHUNK - 1) / CHUNK;                       // in chunks
     if (n_chunks < 16 * warm || ix->n_u < (int64_t)warm * CHUNK) warm = 0;
     // K3b inherits the warm lists and scans only the chunks behind the sample; K3a rescans from chunk 0
@@ -413,7 +416,7 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     a.list_stride = q_pad;
     a.list_q0 = 0;
     a.dbg = nullptr;
-    static unsigned long long *d_dbg = nullptr;
+    unsigned long long *&d_dbg = ix->dbg;
     const char *dbg_env = getenv("GM_TC_DEBUG");
     const bool dbg_on = use_tc && dbg_env && dbg_env[0] == '1';
     if (dbg_on) {
@@ -496,6 +499,20 @@ extern "C" int gm_knn_tune(int queries_per_thread, int splits, int warm_sample) 
     return GM_OK;
 }
 
+extern "C" int gm_index_tune(void *index, int engine, int queries_per_thread, int splits, int warm_sample) {
+    Index *ix = (Index *)index;
+    GM_ARG(ix, "gm_index_tune: NULL index");
+    GM_ARG(engine >= -1 && engine <= 1, "gm_index_tune: engine must be -1 (default), 0 or 1");
+    GM_ARG(queries_per_thread == -1 || queries_per_thread == 4 || queries_per_thread == 8, "gm_index_tune: queries_per_thread must be -1, 4 or 8");
+    GM_ARG(splits >= -1 && splits <= MAX_SPLITS, "gm_index_tune: splits outside [-1,%d]", MAX_SPLITS);
+    GM_ARG(warm_sample >= -2, "gm_index_tune: warm_sample must be >= -2");
+    ix->engine = engine;
+    ix->tune_r = queries_per_thread;
+    ix->tune_splits = splits;
+    ix->tune_warm = warm_sample;
+    return GM_OK;
+}
+
 extern "C" int gm_index_create_dev(const uint64_t *d_uniq2bit, int64_t n_u, int L, int metric, void **index, void *stream) {
     int rc = ensure_init();
     if (rc) return rc;
@@ -566,6 +583,7 @@ extern "C" int gm_index_free(void *index) {
     dev_free(ix->planes, 0);
     dev_free(ix->planes_perm, 0);
     park_ws(ix->ws, ix->ws_bytes);
+    if (ix->dbg) cudaFree(ix->dbg);
     delete ix;
     return GM_OK;
 }

@@ -22,6 +22,9 @@ struct Index {
     int L = 0, metric = 0;
     void *ws = nullptr;
     size_t ws_bytes = 0;
+    // per-handle tuning (gm_index_tune); a negative value follows the process-wide default (gm_knn_tune / gm_knn_engine)
+    int engine = -1, tune_r = -1, tune_splits = -1, tune_warm = -2;
+    unsigned long long *dbg = nullptr;      // GM_TC_DEBUG counters of this index
 };
 
 

@@ -374,11 +374,21 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_emit_records_kernel(const P
 // ---- text columns of the frame, produced from the resident rows and genome ---------------------------------------------
 // `target` (core.py:155,183,209,236): the guide as ASCII, L bytes per row.
 __global__ void __launch_bounds__(256) decode_rows_kernel(const uint64_t *__restrict__ guides, int64_t n_rows, int L, uint8_t *__restrict__ out) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_rows * L) return;
-    const int64_t i = t / L;
-    const int j = (int)(t - i * L);
-    out[t] = (uint8_t)("ACGT"[(guides[i] >> (2 * j)) & 3u]);
+    // four output bytes per thread, one 32-bit store (the text matrix is n_rows x L bytes, row-major, 4-byte aligned)
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = n_rows * L;
+    if (w * 4 >= total) return;
+    int64_t i = (w * 4) / L;
+    int j = (int)(w * 4 - i * L);
+    uint64_t g = guides[i];
+    uint32_t word = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        if (w * 4 + b < total) word |= (uint32_t)(uint8_t)("ACGT"[(g >> (2 * j)) & 3u]) << (8 * b);
+        if (++j == L) { j = 0; i++; if (i < n_rows) g = guides[i]; }
+    }
+    if (w * 4 + 4 <= total) *reinterpret_cast<uint32_t *>(out + w * 4) = word;
+    else for (int b = 0; w * 4 + b < total; b++) out[w * 4 + b] = (uint8_t)(word >> (8 * b));
 }
 
 __constant__ uint8_t c_comp[256];
@@ -386,15 +396,11 @@ __constant__ uint8_t c_comp[256];
 // `target_seq30` (core.py:156,184,210-211,237): the 30-nt slice of the record around the match -- [ms-3, ms+27) for 5prime
 // forward / 3prime reverse hits, [me-27, me+3) for the others -- reverse-complemented for reverse hits, NOT validated.
 // Rows whose window leaves the record are flagged in `edge` and filled with '?': the host applies Python's literal slice
-// semantics to those few rows.
-__global__ void __launch_bounds__(256) context_rows_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ rec_start,
-                                                           const uint32_t *__restrict__ start, const int32_t *__restrict__ rec,
-                                                           const uint8_t *__restrict__ strand, int64_t n_rows, int P, int L,
-                                                           int five_prime, int width, uint8_t *__restrict__ out, uint8_t *__restrict__ edge) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_rows * width) return;
-    const int64_t i = t / width;
-    const int j = (int)(t - i * width);
+// semantics to those few rows.  Four output bytes per thread, one 32-bit store.
+__device__ __forceinline__ uint8_t context_byte(const uint8_t *__restrict__ seq, const int64_t *__restrict__ rec_start,
+                                                const uint32_t *__restrict__ start, const int32_t *__restrict__ rec,
+                                                const uint8_t *__restrict__ strand, int64_t i, int j, int P, int L, int five_prime, int width,
+                                                bool *interior_out) {
     const int r = rec[i];
     const int fwd = strand[i];
     const int64_t st = start[i];
@@ -402,13 +408,33 @@ __global__ void __launch_bounds__(256) context_rows_kernel(const uint8_t *__rest
     const int64_t a = (fwd == five_prime) ? ms - 3 : ms + P - (width - 3);
     const int64_t len = rec_start[r + 1] - rec_start[r] - 1;
     const bool interior = a >= 0 && a + width <= len;
-    uint8_t c = (uint8_t)'?';
-    if (interior) {
-        const int64_t g0 = rec_start[r] + a;
-        c = fwd ? seq[g0 + j] : c_comp[seq[g0 + width - 1 - j]];
+    *interior_out = interior;
+    if (!interior) return (uint8_t)'?';
+    const int64_t g0 = rec_start[r] + a;
+    return fwd ? seq[g0 + j] : c_comp[seq[g0 + width - 1 - j]];
+}
+
+__global__ void __launch_bounds__(256) context_rows_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ rec_start,
+                                                           const uint32_t *__restrict__ start, const int32_t *__restrict__ rec,
+                                                           const uint8_t *__restrict__ strand, int64_t n_rows, int P, int L,
+                                                           int five_prime, int width, uint8_t *__restrict__ out, uint8_t *__restrict__ edge) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = n_rows * width;
+    if (w * 4 >= total) return;
+    int64_t i = (w * 4) / width;
+    int j = (int)(w * 4 - i * width);
+    uint32_t word = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        if (w * 4 + b < total) {
+            bool interior;
+            word |= (uint32_t)context_byte(seq, rec_start, start, rec, strand, i, j, P, L, five_prime, width, &interior) << (8 * b);
+            if (j == 0 && edge) edge[i] = interior ? 0 : 1;
+        }
+        if (++j == width) { j = 0; i++; }
     }
-    out[t] = c;
-    if (j == 0 && edge) edge[i] = interior ? 0 : 1;
+    if (w * 4 + 4 <= total) *reinterpret_cast<uint32_t *>(out + w * 4) = word;
+    else for (int b = 0; w * 4 + b < total; b++) out[w * 4 + b] = (uint8_t)(word >> (8 * b));
 }
 
 static int ensure_comp_table() {
@@ -631,7 +657,7 @@ extern "C" int gm_session_fetch_text(void *session, uint8_t *target_ascii, uint8
     if (target_ascii) {
         e = dev_alloc((void **)&d_t, (size_t)nt * s->L, 0);
         if (e == cudaSuccess) {
-            decode_rows_kernel<<<(unsigned)((nt * s->L + 255) / 256), 256>>>(s->guides, nt, s->L, d_t);
+            decode_rows_kernel<<<(unsigned)(((nt * s->L + 3) / 4 + 255) / 256), 256>>>(s->guides, nt, s->L, d_t);
             count_launch();
             if (trace_on()) { cudaStreamSynchronize(0); trace("  text: decode kernel", t0); }
             prefault(target_ascii, (size_t)nt * s->L);
@@ -643,7 +669,7 @@ extern "C" int gm_session_fetch_text(void *session, uint8_t *target_ascii, uint8
         e = dev_alloc((void **)&d_c, (size_t)nt * width, 0);
         if (e == cudaSuccess && edge) e = dev_alloc((void **)&d_e, (size_t)nt, 0);
         if (e == cudaSuccess) {
-            context_rows_kernel<<<(unsigned)((nt * width + 255) / 256), 256>>>(s->seq, s->rec_start, s->start, s->rec, s->strand, nt, s->P, s->L,
+            context_rows_kernel<<<(unsigned)(((nt * width + 3) / 4 + 255) / 256), 256>>>(s->seq, s->rec_start, s->start, s->rec, s->strand, nt, s->P, s->L,
                                                                                s->five_prime, width, d_c, d_e);
             count_launch();
             if (trace_on()) { cudaStreamSynchronize(0); trace("  text: + D2H target, context kernel", t0); }

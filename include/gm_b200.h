@@ -170,6 +170,20 @@ int gm_min_dist(void *index, const uint64_t *q2bit, int64_t q, uint8_t *out_dist
 int gm_min_dist_dev(void *index, const uint64_t *d_q2bit, int64_t q, uint8_t *d_out_dist,
                     void *stream);
 
+/* ---- multi-GPU: one process per GPU, query rows sharded, guide table replicated -----------------------
+ * The reference has no multi-device path.  Every rank builds the same index (gm_index_create / gm_session_index on its
+ * own GPU), rank 0 makes an id with gm_comm_unique_id and the HOST carries those 128 bytes to the other ranks (MPI, a
+ * file, a socket, torch.distributed ...); each rank then calls gm_comm_create (ncclCommInitRank on the gm_init device).
+ * gm_knn_sharded is gm_knn for all ranks at once: every rank passes the SAME q query rows, uploads and searches only its
+ * contiguous share [rank*q/world ...), the fixed-size (idx, dist) rows are all-gathered device-to-device with
+ * ncclAllGather over NVLink, and every rank receives all q result rows in its host buffers.  NCCL is loaded lazily
+ * (dlopen libnccl.so.2) by the first gm_comm_* call. */
+#define GM_COMM_ID_BYTES 128
+int gm_comm_unique_id(uint8_t *id128);
+int gm_comm_create(const uint8_t *id128, int rank, int world, void **comm);
+int gm_comm_free(void *comm);
+int gm_knn_sharded(void *index, void *comm, const uint64_t *q2bit, int64_t q, int k, int32_t *out_idx, uint8_t *out_dist);
+
 /* ---- measurement hooks ---------------------------------------------------------------------------
  * With profiling on, the library brackets its dominant kernel (the pair-scan of gm_knn*) with
  * CUDA events on the launching stream.  gm_prof_read synchronises those events and returns the
@@ -187,6 +201,9 @@ int gm_knn_tune(int queries_per_thread, int splits, int warm_sample);
  * (default, ~3x faster), 0 = K3a XOR/POPC on the INT pipes.  Both are exact and return identical bits; the
  * Levenshtein metric always uses its own INT-pipe kernel.  DESIGN.md section 3. */
 int gm_knn_engine(int engine);
+/* The same knobs for ONE index handle, overriding the process-wide defaults above: engine -1 / queries_per_thread -1 /
+ * splits -1 / warm_sample -2 = follow the default.  Two indices with different engines can live in one process. */
+int gm_index_tune(void *index, int engine, int queries_per_thread, int splits, int warm_sample);
 
 /* microbenchmarks used as roofline denominators, whole GPU:
  * what = 0: POPC, 1: LOP3, 2: IMAD -> register-resident lane-operations per second;

@@ -408,3 +408,23 @@ def test_knn_hamming_config2_scale_properties(capi_mod, engine):
     og, os_, op, onf, onr = O.c_pam_scan(seq, "NGG", False, 20)
     assert np.array_equal(g, og) and np.array_equal(s, os_) and (nf, nr) == (onf, onr)
     assert np.array_equal(capi.seed_dedup(g, 20, 10, False), O.c_seed_dedup(g, 20, 10, False))
+
+
+def test_per_handle_engine_and_tuning(capi_mod):
+    """two indices with different engines / tunings in one process do not interfere (gm_index_tune), and both return the
+    same bits as the process-default configuration"""
+    rng = np.random.default_rng(31)
+    t, _ = O.unique_first_order(rand_guides(rng, 60000, 20))
+    q = rand_guides(rng, 3000, 20)
+    capi_mod.knn_engine(1)
+    a, b = capi_mod.Index(t, 20, 0), capi_mod.Index(t, 20, 0)
+    a.tune(engine=0, queries_per_thread=4, splits=3, warm_sample=0)      # K3a, explicit splits, no warm start
+    b.tune(engine=1)                                                     # K3b
+    ra, rb = a.knn(q, 5), b.knn(q, 5)
+    ra2 = a.knn(q, 5)                                                    # a's settings survive b's call
+    oi, od = O.c_knn(t, q, 20, 0, 5)
+    for r in (ra, rb, ra2):
+        assert np.array_equal(r[0], oi) and np.array_equal(r[1], od)
+    with pytest.raises(ValueError):
+        a.tune(engine=2)
+    a.close(); b.close()

@@ -22,7 +22,7 @@ uniq = np.ascontiguousarray(g[first == np.arange(len(g))])
 dup = _capi.seed_dedup(g, 20, 10, False)
 q = g if nq <= 0 else g[:nq]
 ix = _capi.Index(uniq, 20, metric)
-_capi.knn_engine(engine)
+ix.tune(engine=engine)                                  # per-handle: 1 = K3b tcgen05, 0 = K3a xor/popc
 for _ in range(2):
     idx, dist = ix.knn(q, 5)
-print("ok", len(g), len(uniq), int(dup.sum()), int(dist[:, 1].min()))
+print("ok", len(g), len(uniq), int(dup.sum()), int(dist[:, 1].min()), "engine", engine, "metric", metric)
