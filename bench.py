@@ -489,8 +489,10 @@ def run_ours(args):
         leven = {"metric": "Levenshtein comparisons/s (20-nt, Myers bit-parallel, K4)", "value": float(nq) * len(u2) / (ms4 * 1e-3),
                  "kernel_comparisons_per_s_per_gpu": rate4, "queries": int(nq), "indexed_guides": int(len(u2)),
                  "cell_updates_per_s_per_gpu": rate4 * GUIDE_LEN * GUIDE_LEN,
-                 "lop3_peak_lane_ops_per_s": lop_rate, "alu_ops_per_comparison_est": 12 * GUIDE_LEN,
-                 "frac_of_alu_peak_est": rate4 * 12 * GUIDE_LEN / lop_rate}
+                 "lop3_peak_lane_ops_per_s": lop_rate, "alu_ops_per_comparison": 7 * GUIDE_LEN,
+                 "frac_of_alu_peak": rate4 * 7 * GUIDE_LEN / lop_rate,
+                 "note": "7 LOP3 (ALU pipe) + 3 IMAD (FMA pipe) per pair and text step, counted in the SASS; peak = LOP3 lane rate measured "
+                         "live (gm_microbench(1)); ncu on the same launch: ALU pipe 84 % (profiles/r02_ncu_full_knn_leven_scan.csv)"}
         r4.close()
 
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------

@@ -52,6 +52,8 @@ _SIGS = {
     "gm_session_index": [_vp, ctypes.c_int, ctypes.POINTER(_vp), _vp, _vp, _c_i64p],
     "gm_session_knn": [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp],
     "gm_session_knn_dev": [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp],
+    "gm_session_neighbors": [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _c_i64p, _c_i64p],
+    "gm_session_fetch_neighbors": [_vp, _vp, _vp, _vp],
     "gm_session_free": [_vp],
     "gm_cfd_scores": [_vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _vp, _vp],
     "gm_restriction_scan": [_vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp],
@@ -238,6 +240,20 @@ class Session:
         idx = np.empty((nq, k), np.int32); dist = np.empty((nq, k), np.uint8)
         _check(load_library().gm_session_knn(self._h, index._h, _p(qmask), nq, int(k), _p(idx), _p(dist)), "gm_session_knn")
         return idx, dist
+
+    def neighbors(self, index: "Index", qmask: np.ndarray, k: int, editdist: int):
+        """get_neighbors on the device: -> (codes u64[m], idx i32[m,k], dist u8[m,k], n_short) for the kept query rows
+        (nearest other guide >= editdist away, first query row of its guide), in row order"""
+        qmask = np.ascontiguousarray(qmask, np.uint8 if qmask.dtype != np.bool_ else np.bool_).view(np.uint8)
+        nq = int(np.count_nonzero(qmask))
+        kept, short = ctypes.c_int64(), ctypes.c_int64()
+        _check(load_library().gm_session_neighbors(self._h, index._h, _p(qmask), nq, int(k), int(editdist), ctypes.byref(kept), ctypes.byref(short)),
+               "gm_session_neighbors")
+        m = kept.value
+        codes = np.empty(m, np.uint64); idx = np.empty((m, k), np.int32); dist = np.empty((m, k), np.uint8)
+        if m:
+            _check(load_library().gm_session_fetch_neighbors(self._h, _p(codes), _p(idx), _p(dist)), "gm_session_fetch_neighbors")
+        return codes, idx, dist, short.value
 
     def knn_dev(self, index: "Index", qmask: np.ndarray, k: int, d_idx: int, d_dist: int, stream: int = 0) -> int:
         """kNN of the masked rows into DEVICE buffers (no synchronisation); returns the number of query rows"""

@@ -39,7 +39,7 @@ import yaml
 from . import _capi
 from ._encode import as_byte_matrix, decode_matrix, encode_matrix, matrix_to_strings
 from .neighbors import ExactIndex, NeighborMap
-from .sharding import broadcast_rank0, sharded_knn, sharded_min_dist, sharded_session_knn
+from .sharding import broadcast_rank0, sharded_knn, sharded_min_dist, sharded_session_knn, world
 
 logger = logging.getLogger(__name__)
 
@@ -424,7 +424,15 @@ class TargetProcessor:
         if len(q) == 0:
             self.neighbors = NeighborMap(q, np.zeros((0, self.knum), np.int32), np.zeros((0, self.knum), np.uint8), index.uniq, L)
             return
-        if sess is not None and hasattr(index._engine, "_h"):  # queries are compacted on the device from the resident rows
+        on_device = sess is not None and hasattr(index._engine, "_h")
+        if on_device and world()[1] == 1 and hasattr(sess, "neighbors"):
+            # single GPU: search, distance filter and one-entry-per-guide rule all on the device; only kept rows come back
+            codes, idx, dist, n_short = sess.neighbors(index._engine, qmask, int(self.knum), int(self.editdist))
+            if int(self.knum) < 2 or n_short:
+                raise IndexError("list index out of range")    # editdist[1] with fewer than 2 hits (core.py:512,518)
+            self.neighbors = NeighborMap(codes, idx, dist, index.uniq, L, final=True)
+            return
+        if on_device:                                          # queries are compacted on the device from the resident rows
             idx, dist = sharded_session_knn(sess, index._engine, qmask, int(self.knum))
         else:
             idx, dist = sharded_knn(index, q, int(self.knum))

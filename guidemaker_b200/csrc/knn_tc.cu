@@ -697,7 +697,10 @@ template <int KC>
 static int launch_tc_kc(dim3 grid, cudaStream_t st, const ScanArgs &a) {
     static bool attr_set = false;
     if (!attr_set) {
-        GM_CUDA(cudaFuncSetAttribute(knn_hamming_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        cudaFuncAttributes fa;
+        GM_CUDA(cudaFuncGetAttributes(&fa, knn_hamming_tc_kernel<KC>));
+        const int room = 227 * 1024 - (int)((fa.sharedSizeBytes + 1023) / 1024 * 1024);     // static arrays come first, dynamic part 1 KB aligned
+        GM_CUDA(cudaFuncSetAttribute(knn_hamming_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, room));
         attr_set = true;
     }
     knn_hamming_tc_kernel<KC><<<grid, TC_THREADS, tc_smem_bytes(KC, a.k), st>>>(a);

@@ -557,6 +557,9 @@ extern "C" int gm_scan_free(void *scan) {
     dev_free(s->seq, 0);
     dev_free(s->rec_start, 0);
     dev_free(s->first32, 0);
+    dev_free(s->nb_codes, 0);
+    dev_free(s->nb_idx, 0);
+    dev_free(s->nb_dist, 0);
     delete s;
     return GM_OK;
 }

@@ -21,6 +21,12 @@ struct Scan {
     int n_rec = 0;
     int P = 0, L = 0, five_prime = 0;
     int32_t *first32 = nullptr;     // after gm_session_index: row -> first row with the same guide
+    // after gm_session_neighbors: the kept query rows (compact), waiting for gm_session_fetch_neighbors
+    uint64_t *nb_codes = nullptr;
+    int32_t *nb_idx = nullptr;
+    uint8_t *nb_dist = nullptr;
+    int64_t nb_rows = 0;
+    int nb_k = 0;
 };
 
 // dedup.cu

@@ -29,6 +29,36 @@ __global__ void uniq_scatter_kernel(const uint64_t *__restrict__ guides, const i
     if (f == (int32_t)i) uniq[r] = guides[i];
 }
 
+// get_neighbors' selection (core.py:505-522) on the device: a query row is kept iff its nearest OTHER guide is at least
+// `editdist` away (dist[1] >= editdist) and it is the first query row carrying its guide (the reference's dict keeps one
+// entry per guide string).  short_rows counts rows with fewer than two hits (the reference raises IndexError there).
+__global__ void neighbor_flag_kernel(const int32_t *__restrict__ idx, const uint8_t *__restrict__ dist, const int32_t *__restrict__ first_q,
+                                     int64_t n_q, int k, int editdist, uint8_t *__restrict__ flag, unsigned long long *__restrict__ short_rows) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_q) return;
+    const bool has2 = k >= 2 && idx[i * k + 1] >= 0;
+    if (!has2) atomicAdd(short_rows, 1ULL);
+    flag[i] = (has2 && (int)dist[i * k + 1] >= editdist && first_q[i] == (int32_t)i) ? 1 : 0;
+}
+
+__global__ void neighbor_gather_kernel(const int32_t *__restrict__ rows, int64_t n_keep, int k, const uint64_t *__restrict__ q,
+                                       const int32_t *__restrict__ idx, const uint8_t *__restrict__ dist, uint64_t *__restrict__ o_codes,
+                                       int32_t *__restrict__ o_idx, uint8_t *__restrict__ o_dist) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_keep * k) return;
+    const int64_t r = t / k;
+    const int j = (int)(t - r * k);
+    const int64_t src = rows[r];
+    o_idx[t] = idx[src * k + j];
+    o_dist[t] = dist[src * k + j];
+    if (j == 0) o_codes[r] = q[src];
+}
+
+__global__ void iota_kernel(int32_t *__restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)i;
+}
+
 static Scan *as_session(void *h) {
     Scan *s = (Scan *)h;
     return (s && s->session) ? s : nullptr;
@@ -215,4 +245,105 @@ extern "C" int gm_session_knn_dev(void *session, void *index, const uint8_t *qma
     int rc = ensure_init();
     if (rc) return rc;
     return session_knn(session, index, qmask, n_q, k, d_out_idx, d_out_dist, true, (cudaStream_t)stream);
+}
+
+// get_neighbors in one call (core.py:495-523): kNN of the masked rows, the distance filter and the one-entry-per-guide
+// rule applied on the device; only the kept rows are copied to the host (gm_session_fetch_neighbors), already compact.
+extern "C" int gm_session_neighbors(void *session, void *index, const uint8_t *qmask, int64_t n_q, int k, int editdist, int64_t *n_kept,
+                                    int64_t *n_short) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    Scan *s = as_session(session);
+    GM_ARG(s && index && qmask && n_kept && n_short, "gm_session_neighbors: bad argument");
+    GM_ARG(k >= 1 && k <= GM_MAX_K, "gm_session_neighbors: k=%d outside [1,%d]", k, GM_MAX_K);
+    *n_kept = *n_short = 0;
+    const int64_t n = s->n_fwd + s->n_rev;
+    if (n == 0 || n_q == 0) return GM_OK;
+    GM_ARG(n_q > 0 && n_q <= n, "gm_session_neighbors: bad n_q");
+    const double t0 = now_ms();
+    cudaStream_t st = 0;
+    dev_free(s->nb_codes, st); dev_free(s->nb_idx, st); dev_free(s->nb_dist, st);
+    s->nb_codes = nullptr; s->nb_idx = nullptr; s->nb_dist = nullptr; s->nb_rows = 0; s->nb_k = k;
+    uint8_t *d_mask = nullptr, *d_dist = nullptr, *d_flag = nullptr;
+    uint64_t *d_q = nullptr;
+    int32_t *d_idx = nullptr, *d_first = nullptr, *d_iota = nullptr, *d_rows = nullptr;
+    unsigned long long *d_cnt = nullptr;          // [0] rows short of two hits, [1] selected-row counter of the compactions
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0, tmp2 = 0;
+    cudaError_t e = dev_alloc((void **)&d_mask, (size_t)n, st);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_q, (size_t)n_q * 8 + 8, st);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_idx, (size_t)n_q * k * 4, st);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_dist, (size_t)n_q * k, st);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_flag, (size_t)n_q, st);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_first, (size_t)n_q * 4, st);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_iota, (size_t)n_q * 4, st);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_rows, (size_t)n_q * 4, st);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_cnt, 16, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, 16, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_mask, qmask, (size_t)n, cudaMemcpyHostToDevice, st);
+    int64_t host_cnt = 0;
+    for (int64_t i = 0; i < n; i++) host_cnt += qmask[i] != 0;
+    if (host_cnt != n_q) { rc = GM_ERR_ARG; set_error("gm_session_neighbors: qmask selects %lld rows, n_q = %lld", (long long)host_cnt, (long long)n_q); }
+    if (rc == GM_OK && e == cudaSuccess) {
+        e = cub::DeviceSelect::Flagged(nullptr, tmp_bytes, s->guides, d_mask, d_q, (long long *)(d_cnt + 1), (int)n, st);
+        if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(nullptr, tmp2, d_iota, d_flag, d_rows, (long long *)(d_cnt + 1), (int)n_q, st);
+        if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
+        if (e == cudaSuccess) e = dev_alloc(&d_tmp, tmp_bytes, st);
+        if (e == cudaSuccess) {
+            if (n_q == n) e = cudaMemcpyAsync(d_q, s->guides, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
+            else { e = cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, s->guides, d_mask, d_q, (long long *)(d_cnt + 1), (int)n, st); count_launch(2); }
+        }
+    }
+    if (rc == GM_OK && e == cudaSuccess) rc = gm_knn_dev(index, d_q, n_q, k, d_idx, d_dist, st);
+    if (rc == GM_OK && e == cudaSuccess) rc = dedup_dev(d_q, n_q, GM_MAX_L, 0, 0, nullptr, nullptr, d_first, st);   // first query row per guide
+    long long kept = 0;
+    unsigned long long short_rows = 0;
+    if (rc == GM_OK && e == cudaSuccess) {
+        const unsigned grid = (unsigned)((n_q + 255) / 256);
+        neighbor_flag_kernel<<<grid, 256, 0, st>>>(d_idx, d_dist, d_first, n_q, k, editdist, d_flag, d_cnt);
+        iota_kernel<<<grid, 256, 0, st>>>(d_iota, n_q);
+        e = cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_iota, d_flag, d_rows, (long long *)(d_cnt + 1), (int)n_q, st);
+        count_launch(4);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&short_rows, d_cnt, 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&kept, d_cnt + 1, 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (rc == GM_OK && e == cudaSuccess && kept > 0) {
+        e = dev_alloc((void **)&s->nb_codes, (size_t)kept * 8, st);
+        if (e == cudaSuccess) e = dev_alloc((void **)&s->nb_idx, (size_t)kept * k * 4, st);
+        if (e == cudaSuccess) e = dev_alloc((void **)&s->nb_dist, (size_t)kept * k, st);
+        if (e == cudaSuccess) {
+            neighbor_gather_kernel<<<(unsigned)((kept * k + 255) / 256), 256, 0, st>>>(d_rows, kept, k, d_q, d_idx, d_dist, s->nb_codes, s->nb_idx, s->nb_dist);
+            count_launch();
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    dev_free(d_mask, st); dev_free(d_q, st); dev_free(d_idx, st); dev_free(d_dist, st); dev_free(d_flag, st); dev_free(d_first, st);
+    dev_free(d_iota, st); dev_free(d_rows, st); dev_free(d_cnt, st); dev_free(d_tmp, st);
+    trace("session: kNN + neighbour filter", t0);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "gm_session_neighbors", __FILE__, __LINE__);
+    s->nb_rows = kept;
+    *n_kept = kept;
+    *n_short = (int64_t)short_rows;
+    return GM_OK;
+}
+
+extern "C" int gm_session_fetch_neighbors(void *session, uint64_t *codes, int32_t *idx, uint8_t *dist) {
+    Scan *s = as_session(session);
+    GM_ARG(s, "gm_session_fetch_neighbors: not a session handle");
+    if (s->nb_rows == 0) return GM_OK;
+    GM_ARG(codes && idx && dist, "gm_session_fetch_neighbors: NULL buffer");
+    const double t0 = now_ms();
+    const size_t r = (size_t)s->nb_rows, k = (size_t)s->nb_k;
+    prefault(codes, r * 8); prefault(idx, r * k * 4); prefault(dist, r * k);
+    GM_CUDA(cudaMemcpyAsync(codes, s->nb_codes, r * 8, cudaMemcpyDeviceToHost, 0));
+    GM_CUDA(cudaMemcpyAsync(idx, s->nb_idx, r * k * 4, cudaMemcpyDeviceToHost, 0));
+    GM_CUDA(cudaMemcpyAsync(dist, s->nb_dist, r * k, cudaMemcpyDeviceToHost, 0));
+    GM_CUDA(cudaStreamSynchronize(0));
+    dev_free(s->nb_codes, 0); dev_free(s->nb_idx, 0); dev_free(s->nb_dist, 0);
+    s->nb_codes = nullptr; s->nb_idx = nullptr; s->nb_dist = nullptr; s->nb_rows = 0;
+    trace("session: fetch neighbours", t0);
+    return GM_OK;
 }

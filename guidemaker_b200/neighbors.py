@@ -73,12 +73,17 @@ class ExactIndex:
 class NeighborMap(Mapping):
     """``neighbors[seq] -> {"target": seq, "neighbors": {"seqs": [...], "dist": [...]}}``."""
 
-    def __init__(self, qcodes: np.ndarray, idx: np.ndarray, dist: np.ndarray, uniq: np.ndarray, L: int, group=None, rows=None):
+    def __init__(self, qcodes: np.ndarray, idx: np.ndarray, dist: np.ndarray, uniq: np.ndarray, L: int, group=None, rows=None, final=False):
         """qcodes/idx/dist: query rows in row order; `rows` (ascending indices, default all) selects the kept ones.
         A dict keyed by the guide string keeps the first row of every distinct guide, in order of first appearance
         (later rows carry identical values).  `group[i]` (one per kept row) = any integer id < len(uniq) that is equal
         for equal guides (e.g. the row's index in the distinct-guide table): with it the dedupe is a linear scatter;
         without it, one stable sort.  The big arrays are gathered once, with the composed index."""
+        if final:                                            # already filtered and one row per guide (gm_session_neighbors)
+            self.codes, self.idx, self.dist = np.ascontiguousarray(qcodes), idx, dist
+            self.uniq, self.L = uniq, int(L)
+            self._sorted = self._pos = None
+            return
         if rows is None:
             rows = np.arange(len(qcodes), dtype=np.int64)
         n = len(rows)

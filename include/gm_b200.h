@@ -131,6 +131,14 @@ int gm_session_index(void *session, int metric, void **index, uint64_t *uniq2bit
 int gm_session_knn(void *session, void *index, const uint8_t *qmask, int64_t n_q, int k, int32_t *out_idx, uint8_t *out_dist);
 int gm_session_knn_dev(void *session, void *index, const uint8_t *qmask, int64_t n_q, int k, int32_t *d_out_idx,
                        uint8_t *d_out_dist, void *stream);
+/* get_neighbors in one call (core.py:495-523): kNN of the masked rows, then -- on the device -- the distance filter
+ * (keep a query iff its nearest OTHER guide is >= editdist away, core.py:512,518) and the one-entry-per-guide rule of the
+ * reference's dict (the first query row of every guide); *n_kept rows stay on the device, *n_short = rows with fewer than
+ * two hits (the reference raises IndexError then).  gm_session_fetch_neighbors copies the kept rows (guide2bit codes,
+ * idx n_kept x k, dist n_kept x k, in row order) and releases them. */
+int gm_session_neighbors(void *session, void *index, const uint8_t *qmask, int64_t n_q, int k, int editdist, int64_t *n_kept,
+                         int64_t *n_short);
+int gm_session_fetch_neighbors(void *session, uint64_t *codes, int32_t *idx, uint8_t *dist);
 int gm_session_free(void *session);
 
 /* ---- K6: restriction-site flag ------------------------------------------------------------------

@@ -101,6 +101,38 @@ def test_session_chain_vs_oracle(capi):
         s.close()
 
 
+def test_session_neighbors_filter_vs_oracle(capi):
+    """gm_session_neighbors: the distance filter (core.py:512,518) and the one-entry-per-guide rule on the device"""
+    rng = np.random.default_rng(91)
+    recs = _genome(rng, [30000, 9000, 25000], gc=0.55)
+    buf, rec_start = _join(recs)
+    s = capi.Session(buf, rec_start, "NGG", False, 20)
+    o = _OracleSession(buf, rec_start, "NGG", False, 20)
+    g = o.g
+    assert len(set(g.tolist())) < len(g)                                # duplicated guides exist
+    ou, _ = O.unique_first_order(g)
+    for metric in (0, 1):
+        ix, uniq, _ = s.build_index(metric)
+        for qmask in (np.ones(len(g), bool), ~o.seed_dedup(10), rng.random(len(g)) < 0.5):
+            for k, editdist in ((5, 2), (2, 4), (3, 0)):
+                codes, idx, dist, n_short = s.neighbors(ix, qmask, k, editdist)
+                oi, od = O.c_knn(ou, g[qmask], 20, metric, k)
+                keep = od[:, 1] >= editdist
+                qg = g[qmask]
+                first = np.zeros(len(qg), bool)
+                first[np.unique(qg, return_index=True)[1]] = True       # first query row of every guide
+                sel = keep & first
+                assert n_short == 0
+                assert np.array_equal(codes, qg[sel]) and np.array_equal(idx, oi[sel]) and np.array_equal(dist, od[sel]), (metric, k, editdist)
+        ix.close()
+    # fewer than two indexed guides: every row is short of a second hit
+    s1 = capi.Session(np.frombuffer(b"ACGTACGTACGTACGTACGTAGG" + b"T" * 30, np.uint8), np.array([0, 54]), "NGG", False, 20)
+    if s1.n_rows == 1:
+        ix1, _, _ = s1.build_index(0)
+        assert s1.neighbors(ix1, np.ones(1, bool), 2, 2)[3] == 1
+    s.close()
+
+
 def test_session_bad_arguments(capi):
     buf, rec_start = _join([b"ACGT" * 50])
     with pytest.raises(ValueError):
@@ -227,3 +259,16 @@ def test_fuzz_knn_bounded():
     """tools/fuzz_knn.py for ~20 s: random table sizes, query counts, k and L; K3b = K3a = oracle on every case"""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_knn.py"), "20", "12"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "all identical to the oracle" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_knn_sharded_through_the_c_abi():
+    """gm_comm_* + gm_knn_sharded (NCCL bound lazily inside the library): tools/comm_check.py under torchrun with as many
+    ranks as there are GPUs (at most 2; one rank still runs ncclCommInitRank / ncclAllGather).  Every rank must get the
+    full, oracle-exact table."""
+    import torch
+    world = max(1, min(2, torch.cuda.device_count()))
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "tools", "comm_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and all("COMM_OK %d" % i in r.stdout for i in range(world)), r.stdout[-3000:] + r.stderr[-3000:]

@@ -20,7 +20,7 @@ comm = _capi.Comm(box[0], rank, world)
 rng = np.random.default_rng(3)
 t = np.unique(rng.integers(0, 1 << 40, size=400000, dtype=np.uint64))
 ok = True
-for nq in (1, world - 1, 1001, 250007):
+for nq in (1, max(world - 1, 1), 1001, 250007):
     q = np.concatenate([t[: nq // 2], rng.integers(0, 1 << 40, size=nq - nq // 2, dtype=np.uint64)])
     ix = _capi.Index(t, 20, 0)
     t0 = time.perf_counter()
