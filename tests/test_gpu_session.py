@@ -104,7 +104,7 @@ def test_session_chain_vs_oracle(capi):
 def test_session_neighbors_filter_vs_oracle(capi):
     """gm_session_neighbors: the distance filter (core.py:512,518) and the one-entry-per-guide rule on the device"""
     rng = np.random.default_rng(91)
-    recs = _genome(rng, [30000, 9000, 25000], gc=0.55)
+    recs = _genome(rng, [9000, 4000, 7000], gc=0.55)
     buf, rec_start = _join(recs)
     s = capi.Session(buf, rec_start, "NGG", False, 20)
     o = _OracleSession(buf, rec_start, "NGG", False, 20)
