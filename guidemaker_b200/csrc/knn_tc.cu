@@ -177,13 +177,25 @@ __device__ __noinline__ void tc_watchdog(int what) {
     printf("libgm_b200: K3b watchdog %d fired (block %d,%d thread %d)\n", what, blockIdx.x, blockIdx.y, threadIdx.x);
     __trap();
 }
-// mbarrier wait for the role loops: the first try is inline, the spin (with its watchdog: clock, counter, printf
-// arguments) lives in an outlined function so that it costs the callers no registers.
+// mbarrier wait for the role loops: the first try is inline, the retry loop lives in an outlined function so that it
+// costs the callers no registers.  The retry passes a suspend-time hint (the warp stays suspended until the phase completes
+// or ~1 ms passes, instead of the short default limit) and the loop body is three instructions: in the round-1 form
+// (default limit, clock64() watchdog in every iteration: 15 instructions) the retry loops were 25 % of ALL warp
+// instructions the kernel executed (ncu source page, profiles/r02_ncu_full_knn_hamming_tc_c5.csv) -- issue slots the
+// producers and the read-out warps compete for.  The watchdog counts retries: 2^14 x ~1 ms ~ 16 s.
+__device__ __forceinline__ bool mbar_try_wait_long(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
+    return ok != 0;
+}
 __device__ __noinline__ void tc_wait_slow(uint64_t *bar, uint32_t parity) {
-    const long long t0 = clock64();
     uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity))
-        if ((++spins & 0xFFFu) == 0 && clock64() - t0 > 20000000000LL) tc_watchdog(3);
+    while (!mbar_try_wait_long(bar, parity))
+        if (++spins == (1u << 14)) tc_watchdog(3);
 }
 __device__ __forceinline__ void tc_wait(uint64_t *bar, uint32_t parity) {
     if (!mbar_try_wait(bar, parity)) tc_wait_slow(bar, parity);
