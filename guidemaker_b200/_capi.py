@@ -53,6 +53,7 @@ _SIGS = {
     "gm_session_knn": [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp],
     "gm_session_knn_dev": [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp],
     "gm_session_neighbors": [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _c_i64p, _c_i64p],
+    "gm_session_filter_dev": [_vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _c_i64p, _c_i64p],
     "gm_session_fetch_neighbors": [_vp, _vp, _vp, _vp],
     "gm_session_free": [_vp],
     "gm_cfd_scores": [_vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _vp, _vp],
@@ -249,6 +250,19 @@ class Session:
         kept, short = ctypes.c_int64(), ctypes.c_int64()
         _check(load_library().gm_session_neighbors(self._h, index._h, _p(qmask), nq, int(k), int(editdist), ctypes.byref(kept), ctypes.byref(short)),
                "gm_session_neighbors")
+        m = kept.value
+        codes = np.empty(m, np.uint64); idx = np.empty((m, k), np.int32); dist = np.empty((m, k), np.uint8)
+        if m:
+            _check(load_library().gm_session_fetch_neighbors(self._h, _p(codes), _p(idx), _p(dist)), "gm_session_fetch_neighbors")
+        return codes, idx, dist, short.value
+
+    def filter_dev(self, qmask: np.ndarray, k: int, editdist: int, d_idx: int, d_dist: int, stream: int = 0):
+        """the selection of `neighbors` for (idx, dist) rows already on the device (all masked rows, row order)"""
+        qmask = np.ascontiguousarray(qmask, np.uint8 if qmask.dtype != np.bool_ else np.bool_).view(np.uint8)
+        nq = int(np.count_nonzero(qmask))
+        kept, short = ctypes.c_int64(), ctypes.c_int64()
+        _check(load_library().gm_session_filter_dev(self._h, _p(qmask), nq, int(k), int(editdist), _vp(d_idx), _vp(d_dist), _vp(stream),
+                                                    ctypes.byref(kept), ctypes.byref(short)), "gm_session_filter_dev")
         m = kept.value
         codes = np.empty(m, np.uint64); idx = np.empty((m, k), np.int32); dist = np.empty((m, k), np.uint8)
         if m:

@@ -39,7 +39,8 @@ import yaml
 from . import _capi
 from ._encode import as_byte_matrix, decode_matrix, encode_matrix, matrix_to_strings
 from .neighbors import ExactIndex, NeighborMap
-from .sharding import broadcast_rank0, sharded_knn, sharded_min_dist, sharded_session_knn, world
+from .sharding import (broadcast_rank0, nccl_group, sharded_knn, sharded_min_dist, sharded_session_knn,
+                       sharded_session_neighbors, world)
 
 logger = logging.getLogger(__name__)
 
@@ -425,9 +426,13 @@ class TargetProcessor:
             self.neighbors = NeighborMap(q, np.zeros((0, self.knum), np.int32), np.zeros((0, self.knum), np.uint8), index.uniq, L)
             return
         on_device = sess is not None and hasattr(index._engine, "_h")
-        if on_device and world()[1] == 1 and hasattr(sess, "neighbors"):
-            # single GPU: search, distance filter and one-entry-per-guide rule all on the device; only kept rows come back
-            codes, idx, dist, n_short = sess.neighbors(index._engine, qmask, int(self.knum), int(self.editdist))
+        if on_device and hasattr(sess, "neighbors") and (world()[1] == 1 or nccl_group()):
+            # search, distance filter and one-entry-per-guide rule all on the device; only kept rows come back (several
+            # ranks: shards searched and all-gathered on the devices first, every rank filters the gathered table)
+            if world()[1] == 1:
+                codes, idx, dist, n_short = sess.neighbors(index._engine, qmask, int(self.knum), int(self.editdist))
+            else:
+                codes, idx, dist, n_short = sharded_session_neighbors(sess, index._engine, qmask, int(self.knum), int(self.editdist))
             if int(self.knum) < 2 or n_short:
                 raise IndexError("list index out of range")    # editdist[1] with fewer than 2 hits (core.py:512,518)
             self.neighbors = NeighborMap(codes, idx, dist, index.uniq, L, final=True)

@@ -247,57 +247,29 @@ extern "C" int gm_session_knn_dev(void *session, void *index, const uint8_t *qma
     return session_knn(session, index, qmask, n_q, k, d_out_idx, d_out_dist, true, (cudaStream_t)stream);
 }
 
-// get_neighbors in one call (core.py:495-523): kNN of the masked rows, the distance filter and the one-entry-per-guide
-// rule applied on the device; only the kept rows are copied to the host (gm_session_fetch_neighbors), already compact.
-extern "C" int gm_session_neighbors(void *session, void *index, const uint8_t *qmask, int64_t n_q, int k, int editdist, int64_t *n_kept,
-                                    int64_t *n_short) {
-    int rc = ensure_init();
-    if (rc) return rc;
-    Scan *s = as_session(session);
-    GM_ARG(s && index && qmask && n_kept && n_short, "gm_session_neighbors: bad argument");
-    GM_ARG(k >= 1 && k <= GM_MAX_K, "gm_session_neighbors: k=%d outside [1,%d]", k, GM_MAX_K);
-    *n_kept = *n_short = 0;
-    const int64_t n = s->n_fwd + s->n_rev;
-    if (n == 0 || n_q == 0) return GM_OK;
-    GM_ARG(n_q > 0 && n_q <= n, "gm_session_neighbors: bad n_q");
-    const double t0 = now_ms();
-    cudaStream_t st = 0;
+// The selection of get_neighbors (core.py:505-522) for kNN rows that are already on the device: d_q = the n_q query codes
+// in row order, d_idx / d_dist = their (idx, dist) rows.  Leaves the kept rows compact in the session (nb_*).
+static int neighbors_filter(Scan *s, const uint64_t *d_q, int64_t n_q, int k, int editdist, const int32_t *d_idx, const uint8_t *d_dist,
+                            cudaStream_t st, int64_t *n_kept, int64_t *n_short) {
     dev_free(s->nb_codes, st); dev_free(s->nb_idx, st); dev_free(s->nb_dist, st);
     s->nb_codes = nullptr; s->nb_idx = nullptr; s->nb_dist = nullptr; s->nb_rows = 0; s->nb_k = k;
-    uint8_t *d_mask = nullptr, *d_dist = nullptr, *d_flag = nullptr;
-    uint64_t *d_q = nullptr;
-    int32_t *d_idx = nullptr, *d_first = nullptr, *d_iota = nullptr, *d_rows = nullptr;
-    unsigned long long *d_cnt = nullptr;          // [0] rows short of two hits, [1] selected-row counter of the compactions
+    uint8_t *d_flag = nullptr;
+    int32_t *d_first = nullptr, *d_iota = nullptr, *d_rows = nullptr;
+    unsigned long long *d_cnt = nullptr;          // [0] rows short of two hits, [1] kept rows
     void *d_tmp = nullptr;
-    size_t tmp_bytes = 0, tmp2 = 0;
-    cudaError_t e = dev_alloc((void **)&d_mask, (size_t)n, st);
-    if (e == cudaSuccess) e = dev_alloc((void **)&d_q, (size_t)n_q * 8 + 8, st);
-    if (e == cudaSuccess) e = dev_alloc((void **)&d_idx, (size_t)n_q * k * 4, st);
-    if (e == cudaSuccess) e = dev_alloc((void **)&d_dist, (size_t)n_q * k, st);
-    if (e == cudaSuccess) e = dev_alloc((void **)&d_flag, (size_t)n_q, st);
+    size_t tmp_bytes = 0;
+    long long kept = 0;
+    unsigned long long short_rows = 0;
+    int rc = GM_OK;
+    cudaError_t e = dev_alloc((void **)&d_flag, (size_t)n_q, st);
     if (e == cudaSuccess) e = dev_alloc((void **)&d_first, (size_t)n_q * 4, st);
     if (e == cudaSuccess) e = dev_alloc((void **)&d_iota, (size_t)n_q * 4, st);
     if (e == cudaSuccess) e = dev_alloc((void **)&d_rows, (size_t)n_q * 4, st);
     if (e == cudaSuccess) e = dev_alloc((void **)&d_cnt, 16, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, 16, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_mask, qmask, (size_t)n, cudaMemcpyHostToDevice, st);
-    int64_t host_cnt = 0;
-    for (int64_t i = 0; i < n; i++) host_cnt += qmask[i] != 0;
-    if (host_cnt != n_q) { rc = GM_ERR_ARG; set_error("gm_session_neighbors: qmask selects %lld rows, n_q = %lld", (long long)host_cnt, (long long)n_q); }
-    if (rc == GM_OK && e == cudaSuccess) {
-        e = cub::DeviceSelect::Flagged(nullptr, tmp_bytes, s->guides, d_mask, d_q, (long long *)(d_cnt + 1), (int)n, st);
-        if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(nullptr, tmp2, d_iota, d_flag, d_rows, (long long *)(d_cnt + 1), (int)n_q, st);
-        if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
-        if (e == cudaSuccess) e = dev_alloc(&d_tmp, tmp_bytes, st);
-        if (e == cudaSuccess) {
-            if (n_q == n) e = cudaMemcpyAsync(d_q, s->guides, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
-            else { e = cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, s->guides, d_mask, d_q, (long long *)(d_cnt + 1), (int)n, st); count_launch(2); }
-        }
-    }
-    if (rc == GM_OK && e == cudaSuccess) rc = gm_knn_dev(index, d_q, n_q, k, d_idx, d_dist, st);
-    if (rc == GM_OK && e == cudaSuccess) rc = dedup_dev(d_q, n_q, GM_MAX_L, 0, 0, nullptr, nullptr, d_first, st);   // first query row per guide
-    long long kept = 0;
-    unsigned long long short_rows = 0;
+    if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(nullptr, tmp_bytes, d_iota, d_flag, d_rows, (long long *)(d_cnt + 1), (int)n_q, st);
+    if (e == cudaSuccess) e = dev_alloc(&d_tmp, tmp_bytes, st);
+    if (e == cudaSuccess) rc = dedup_dev(d_q, n_q, GM_MAX_L, 0, 0, nullptr, nullptr, d_first, st);   // first query row per guide
     if (rc == GM_OK && e == cudaSuccess) {
         const unsigned grid = (unsigned)((n_q + 255) / 256);
         neighbor_flag_kernel<<<grid, 256, 0, st>>>(d_idx, d_dist, d_first, n_q, k, editdist, d_flag, d_cnt);
@@ -319,15 +291,92 @@ extern "C" int gm_session_neighbors(void *session, void *index, const uint8_t *q
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     }
-    dev_free(d_mask, st); dev_free(d_q, st); dev_free(d_idx, st); dev_free(d_dist, st); dev_free(d_flag, st); dev_free(d_first, st);
-    dev_free(d_iota, st); dev_free(d_rows, st); dev_free(d_cnt, st); dev_free(d_tmp, st);
-    trace("session: kNN + neighbour filter", t0);
+    dev_free(d_flag, st); dev_free(d_first, st); dev_free(d_iota, st); dev_free(d_rows, st); dev_free(d_cnt, st); dev_free(d_tmp, st);
     if (rc) return rc;
-    if (e != cudaSuccess) return cuda_fail(e, "gm_session_neighbors", __FILE__, __LINE__);
+    if (e != cudaSuccess) return cuda_fail(e, "neighbour filter", __FILE__, __LINE__);
     s->nb_rows = kept;
     *n_kept = kept;
     *n_short = (int64_t)short_rows;
     return GM_OK;
+}
+
+// compaction of the masked rows' guides: d_q[0 .. n_q) = guides[qmask != 0]
+static int masked_queries(Scan *s, const uint8_t *qmask, int64_t n_q, uint64_t *d_q, cudaStream_t st) {
+    const int64_t n = s->n_fwd + s->n_rev;
+    int64_t host_cnt = 0;
+    for (int64_t i = 0; i < n; i++) host_cnt += qmask[i] != 0;
+    if (host_cnt != n_q) { set_error("qmask selects %lld rows, n_q = %lld", (long long)host_cnt, (long long)n_q); return GM_ERR_ARG; }
+    if (n_q == n) { GM_CUDA(cudaMemcpyAsync(d_q, s->guides, (size_t)n * 8, cudaMemcpyDeviceToDevice, st)); return GM_OK; }
+    uint8_t *d_mask = nullptr;
+    long long *d_cnt = nullptr;
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cudaError_t e = dev_alloc((void **)&d_mask, (size_t)n, st);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_cnt, 8, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_mask, qmask, (size_t)n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(nullptr, tmp_bytes, s->guides, d_mask, d_q, d_cnt, (int)n, st);
+    if (e == cudaSuccess) e = dev_alloc(&d_tmp, tmp_bytes, st);
+    if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, s->guides, d_mask, d_q, d_cnt, (int)n, st);
+    count_launch(2);
+    dev_free(d_mask, st); dev_free(d_cnt, st); dev_free(d_tmp, st);
+    if (e != cudaSuccess) return cuda_fail(e, "query compaction", __FILE__, __LINE__);
+    return GM_OK;
+}
+
+// get_neighbors in one call (core.py:495-523): kNN of the masked rows, the distance filter and the one-entry-per-guide
+// rule applied on the device; only the kept rows are copied to the host (gm_session_fetch_neighbors), already compact.
+extern "C" int gm_session_neighbors(void *session, void *index, const uint8_t *qmask, int64_t n_q, int k, int editdist, int64_t *n_kept,
+                                    int64_t *n_short) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    Scan *s = as_session(session);
+    GM_ARG(s && index && qmask && n_kept && n_short, "gm_session_neighbors: bad argument");
+    GM_ARG(k >= 1 && k <= GM_MAX_K, "gm_session_neighbors: k=%d outside [1,%d]", k, GM_MAX_K);
+    *n_kept = *n_short = 0;
+    const int64_t n = s->n_fwd + s->n_rev;
+    if (n == 0 || n_q == 0) return GM_OK;
+    GM_ARG(n_q > 0 && n_q <= n, "gm_session_neighbors: bad n_q");
+    const double t0 = now_ms();
+    cudaStream_t st = 0;
+    uint64_t *d_q = nullptr;
+    int32_t *d_idx = nullptr;
+    uint8_t *d_dist = nullptr;
+    cudaError_t e = dev_alloc((void **)&d_q, (size_t)n_q * 8 + 8, st);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_idx, (size_t)n_q * k * 4, st);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_dist, (size_t)n_q * k, st);
+    if (e == cudaSuccess) rc = masked_queries(s, qmask, n_q, d_q, st);
+    if (rc == GM_OK && e == cudaSuccess) rc = gm_knn_dev(index, d_q, n_q, k, d_idx, d_dist, st);
+    if (rc == GM_OK && e == cudaSuccess) rc = neighbors_filter(s, d_q, n_q, k, editdist, d_idx, d_dist, st, n_kept, n_short);
+    dev_free(d_q, st); dev_free(d_idx, st); dev_free(d_dist, st);
+    trace("session: kNN + neighbour filter", t0);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "gm_session_neighbors", __FILE__, __LINE__);
+    return GM_OK;
+}
+
+// The same selection for kNN rows the caller already holds on the device -- the multi-GPU path: every rank searches its
+// shard (gm_session_knn_dev), the rows are all-gathered device to device, and each rank filters the gathered table here.
+// d_idx / d_dist: n_q x k rows in query-row order (device); enqueued on `stream`, synchronised before returning.
+extern "C" int gm_session_filter_dev(void *session, const uint8_t *qmask, int64_t n_q, int k, int editdist, const int32_t *d_idx,
+                                     const uint8_t *d_dist, void *stream, int64_t *n_kept, int64_t *n_short) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    Scan *s = as_session(session);
+    GM_ARG(s && qmask && d_idx && d_dist && n_kept && n_short, "gm_session_filter_dev: bad argument");
+    GM_ARG(k >= 1 && k <= GM_MAX_K, "gm_session_filter_dev: k=%d outside [1,%d]", k, GM_MAX_K);
+    *n_kept = *n_short = 0;
+    const int64_t n = s->n_fwd + s->n_rev;
+    if (n == 0 || n_q == 0) return GM_OK;
+    GM_ARG(n_q > 0 && n_q <= n, "gm_session_filter_dev: bad n_q");
+    const double t0 = now_ms();
+    cudaStream_t st = (cudaStream_t)stream;
+    uint64_t *d_q = nullptr;
+    GM_CUDA(dev_alloc((void **)&d_q, (size_t)n_q * 8 + 8, st));
+    rc = masked_queries(s, qmask, n_q, d_q, st);
+    if (rc == GM_OK) rc = neighbors_filter(s, d_q, n_q, k, editdist, d_idx, d_dist, st, n_kept, n_short);
+    dev_free(d_q, st);
+    trace("session: neighbour filter (gathered rows)", t0);
+    return rc;
 }
 
 extern "C" int gm_session_fetch_neighbors(void *session, uint64_t *codes, int32_t *idx, uint8_t *dist) {

@@ -27,6 +27,14 @@ def world():
     return 0, 1
 
 
+def nccl_group() -> bool:
+    """True iff a torch.distributed group with the NCCL backend is initialised (device-side collectives possible)"""
+    if world()[1] == 1:
+        return False
+    import torch.distributed as dist
+    return dist.get_backend() == "nccl"
+
+
 def shard_bounds(n: int, rank: int, world_size: int):
     """Contiguous, balanced row range of `rank`: sizes differ by at most one."""
     base, rem = divmod(int(n), int(world_size))
@@ -92,27 +100,20 @@ def _pinned_like(name: str, shape, dtype):
     return buf[1]
 
 
-def sharded_session_knn(sess, engine, qmask: np.ndarray, k: int):
-    """kNN of the masked rows of a device-resident scan (``_capi.Session``) with the query rows split over the ranks.
-
-    Single process: one call, results straight into host arrays.  NCCL: every rank compacts and searches ITS slice of
-    the query rows on the device, the fixed-size result rows are all-gathered device-to-device, and only then copied
-    once into page-locked host memory -- nothing bounces through the host between the kernel and the collective."""
-    rank, ws = world()
-    if ws == 1:
-        return sess.knn(engine, qmask, k)
+def _session_gather_dev(sess, engine, qmask: np.ndarray, k: int):
+    """NCCL path: every rank compacts and searches ITS slice of the query rows on the device; the fixed-size result rows
+    are all-gathered device to device.  -> (idx, dist) torch tensors [nq, k] on the device, query-row order."""
     import torch
     import torch.distributed as dist
+    rank, ws = world()
     qrows = np.flatnonzero(qmask)
     nq = len(qrows)
     lo, hi = shard_bounds(nq, rank, ws)
     local = np.zeros(len(qmask), np.uint8)
     local[qrows[lo:hi]] = 1
-    if dist.get_backend() != "nccl":                          # CPU test plumbing (gloo): host arrays through _gather_rows
-        idx, dist_ = sess.knn(engine, local, k)
-        return _gather_rows(idx, nq, rank, ws), _gather_rows(dist_, nq, rank, ws)
     dev = torch.device("cuda", torch.cuda.current_device())
-    rows = max(shard_bounds(nq, r, ws)[1] - shard_bounds(nq, r, ws)[0] for r in range(ws))
+    sizes = [shard_bounds(nq, r, ws)[1] - shard_bounds(nq, r, ws)[0] for r in range(ws)]
+    rows = max(sizes)
     d_idx = torch.full((rows, k), -1, dtype=torch.int32, device=dev)
     d_dist = torch.full((rows, k), 255, dtype=torch.uint8, device=dev)
     g_idx = torch.empty((ws * rows, k), dtype=torch.int32, device=dev)
@@ -121,17 +122,47 @@ def sharded_session_knn(sess, engine, qmask: np.ndarray, k: int):
     sess.knn_dev(engine, local, k, d_idx.data_ptr(), d_dist.data_ptr(), stream)
     dist.all_gather_into_tensor(g_idx, d_idx)
     dist.all_gather_into_tensor(g_dist, d_dist)
+    if nq != ws * rows:                                     # unequal shards: drop the padding rows (on the device)
+        g_idx = torch.cat([g_idx[r * rows: r * rows + sizes[r]] for r in range(ws)])
+        g_dist = torch.cat([g_dist[r * rows: r * rows + sizes[r]] for r in range(ws)])
+    return g_idx, g_dist
+
+
+def sharded_session_knn(sess, engine, qmask: np.ndarray, k: int):
+    """kNN of the masked rows of a device-resident scan (``_capi.Session``) with the query rows split over the ranks.
+
+    Single process: one call, results straight into host arrays.  NCCL: shards searched and gathered on the devices
+    (``_session_gather_dev``), then copied once into page-locked host memory -- nothing bounces through the host between
+    the kernel and the collective."""
+    rank, ws = world()
+    if ws == 1:
+        return sess.knn(engine, qmask, k)
+    import torch
+    import torch.distributed as dist
+    if dist.get_backend() != "nccl":                          # CPU test plumbing (gloo): host arrays through _gather_rows
+        qrows = np.flatnonzero(qmask)
+        lo, hi = shard_bounds(len(qrows), rank, ws)
+        local = np.zeros(len(qmask), np.uint8)
+        local[qrows[lo:hi]] = 1
+        idx, dist_ = sess.knn(engine, local, k)
+        return _gather_rows(idx, len(qrows), rank, ws), _gather_rows(dist_, len(qrows), rank, ws)
+    g_idx, g_dist = _session_gather_dev(sess, engine, qmask, k)
     h_idx = _pinned_like("idx", g_idx.shape, torch.int32)
     h_dist = _pinned_like("dist", g_dist.shape, torch.uint8)
     h_idx.copy_(g_idx, non_blocking=True)
     h_dist.copy_(g_dist, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    out_i, out_d = h_idx.numpy().reshape(ws, rows, k), h_dist.numpy().reshape(ws, rows, k)
-    if nq == ws * rows:
-        return out_i.reshape(nq, k).copy(), out_d.reshape(nq, k).copy()
-    sizes = [shard_bounds(nq, r, ws)[1] - shard_bounds(nq, r, ws)[0] for r in range(ws)]
-    return (np.concatenate([out_i[r, : sizes[r]] for r in range(ws)], axis=0),
-            np.concatenate([out_d[r, : sizes[r]] for r in range(ws)], axis=0))
+    return h_idx.numpy().copy(), h_dist.numpy().copy()
+
+
+def sharded_session_neighbors(sess, engine, qmask: np.ndarray, k: int, editdist: int):
+    """get_neighbors' selection with the search sharded over the ranks: gather the rows on the devices, then every rank
+    filters the gathered table on its own GPU (``gm_session_filter_dev``) and copies only the kept rows to the host.
+    -> (codes, idx, dist, n_short) as ``Session.neighbors``."""
+    import torch
+    g_idx, g_dist = _session_gather_dev(sess, engine, qmask, k)
+    stream = torch.cuda.current_stream().cuda_stream
+    return sess.filter_dev(qmask, k, editdist, g_idx.data_ptr(), g_dist.data_ptr(), stream)
 
 
 def sharded_min_dist(index, q2bit: np.ndarray) -> np.ndarray:

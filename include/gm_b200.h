@@ -138,6 +138,9 @@ int gm_session_knn_dev(void *session, void *index, const uint8_t *qmask, int64_t
  * idx n_kept x k, dist n_kept x k, in row order) and releases them. */
 int gm_session_neighbors(void *session, void *index, const uint8_t *qmask, int64_t n_q, int k, int editdist, int64_t *n_kept,
                          int64_t *n_short);
+/* the same selection for kNN rows already on the device (n_q x k, query-row order) -- multi-GPU: after the all-gather */
+int gm_session_filter_dev(void *session, const uint8_t *qmask, int64_t n_q, int k, int editdist, const int32_t *d_idx,
+                          const uint8_t *d_dist, void *stream, int64_t *n_kept, int64_t *n_short);
 int gm_session_fetch_neighbors(void *session, uint64_t *codes, int32_t *idx, uint8_t *dist);
 int gm_session_free(void *session);
 

@@ -272,3 +272,16 @@ def test_knn_sharded_through_the_c_abi():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
                         "--master-port", str(port), os.path.join(ROOT, "tools", "comm_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and all("COMM_OK %d" % i in r.stdout for i in range(world)), r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_public_api_under_nccl_ranks():
+    """tools/api_nccl_check.py under torchrun with 2 ranks (skipped on a single-GPU box): sharded search, device-side gather
+    and neighbour filter, rank 0's controls -- every rank ends with the oracle-exact tables"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "tools", "api_nccl_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "API_NCCL_OK 0" in r.stdout and "API_NCCL_OK 1" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
