@@ -68,6 +68,9 @@ namespace gm {
 static constexpr int TC_M = 128;           // rows per A operand
 static constexpr int TC_N = 128;           // targets per tile
 static constexpr int TC_SETS = 2;          // A operands (query tiles) per CTA
+#ifndef GM_TC_TOKEN_FENCE
+#define GM_TC_TOKEN_FENCE 0
+#endif
 #ifndef GM_TC_STAGES
 #define GM_TC_STAGES 6
 #endif
@@ -483,7 +486,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
 #pragma unroll
                 for (int ks = 0; ks < ((GM_TC_ABL & 4) ? 0 : (GM_TC_ABL & 256) ? n_ks - 1 : n_ks); ks++)
                     tc_mma_i8(d, da + (uint64_t)((uint32_t)ks * a_ks), db + (uint64_t)((uint32_t)ks * b_ks), idesc, ks > 0 ? 1u : 0u);
+#if GM_TC_TOKEN_FENCE
                 __threadfence_block();
+#endif
                 st_vol(&s_issued[q], (uint32_t)i + 1u);             // the set's other issuer may go ahead
                 tc_commit_addr(bar_f);                              // accumulator buffer ready for its epilogue warps (which
                                                                     // also release the smem stage)
