@@ -455,7 +455,7 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
             if (rc) return rc;
         }
         if (dbg_on) {
-            unsigned long long h[56];
+            unsigned long long h[96];
             GM_CUDA(cudaStreamSynchronize(st));
             GM_CUDA(cudaMemcpy(h, d_dbg, sizeof h, cudaMemcpyDeviceToHost));
             // (the counters are compiled in with -DGM_TC_STATS, see tools/tc_ablate.py; otherwise they read 0)
@@ -463,6 +463,17 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
                     "epilogue warps: %.1f %% of their time behind a full candidate queue (%llu stalls)\n", h[0],
                     (double)h[0] / (double)q, h[1], (double)h[1] / (double)q, (unsigned)(q_pad / tc_query_tile()), tail_tiles ? tail_splits : splits,
                     h[4] ? 100.0 * (double)h[2] / (double)h[4] : 0.0, h[3]);
+            {   // per role: share of its warps' lifetime spent inside each wait (GM_TC_STATS)
+                const char *role[4] = {"read-out", "producer", "issuer", "candidate"};
+                const char *what[4][3] = {{"acc_full", "-", "-"}, {"b_empty", "-", "-"}, {"b_full", "acc_empty", "issue token"}, {"-", "-", "-"}};
+                for (int r = 0; r < 3; r++) {
+                    const double life = (double)h[64 + r * 4 + 3];
+                    fprintf(stderr, "[tc_dbg] %s warps wait:", role[r]);
+                    for (int w = 0; w < 3; w++)
+                        if (what[r][w][0] != '-') fprintf(stderr, " %s %.1f %%", what[r][w], life > 0 ? 100.0 * (double)h[64 + r * 4 + w] / life : 0.0);
+                    fprintf(stderr, "\n");
+                }
+            }
             fprintf(stderr, "[tc_dbg] cycles per tile over successive 256-tile windows of CTA 200:");
             for (int w = 1; w < 48 && h[8 + w]; w++) fprintf(stderr, " %.0f", (double)(h[8 + w] - h[8 + w - 1]) / 256.0);
             fprintf(stderr, "\n");

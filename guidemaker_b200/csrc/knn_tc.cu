@@ -203,6 +203,17 @@ __device__ __noinline__ void tc_wait_slow(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void tc_wait(uint64_t *bar, uint32_t parity) {
     if (!mbar_try_wait(bar, parity)) tc_wait_slow(bar, parity);
 }
+// -DGM_TC_STATS: cycles a role spends inside a wait, accumulated per call site (slot) for the whole grid
+#ifdef GM_TC_STATS
+#define TC_WAIT_T(slot, bar, parity)                                                                      \
+    do {                                                                                                  \
+        const long long w0__ = clock64();                                                                 \
+        tc_wait(bar, parity);                                                                             \
+        if (lane == 0 && a.dbg) wait_clk[slot] += (unsigned long long)(clock64() - w0__);                 \
+    } while (0)
+#else
+#define TC_WAIT_T(slot, bar, parity) tc_wait(bar, parity)
+#endif
 // OR of 16 registers as a depth-3 tree of 3-input LOP3s (a serial chain would be 8 deep)
 __device__ __forceinline__ uint32_t tc_or16(const uint32_t *r) {
     const uint32_t a = r[0] | r[1] | r[2], b = r[3] | r[4] | r[5], c = r[6] | r[7] | r[8], d = r[9] | r[10] | r[11], e = r[12] | r[13] | r[14];
@@ -329,6 +340,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
+#ifdef GM_TC_STATS
+    unsigned long long wait_clk[4] = {0, 0, 0, 0};      // per role: [0..1] its waits, [2] loop time
+    const long long role_t0 = clock64();
+#endif
 
     if (warp < TC_EPI_WARPS) {
         // ================= epilogue: (set, buffer, quadrant) = (warp >> 3, (warp >> 2) & 1, warp & 3) ===================
@@ -342,7 +357,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
 #endif
         uint32_t r[32];
         for (int i = par; i < n_tiles; i += 2) {
-            tc_wait(&acc_full[set][par], (uint32_t)((i >> 1) & 1));
+            TC_WAIT_T(0, &acc_full[set][par], (uint32_t)((i >> 1) & 1));
             tc_fence_after();
 #ifdef GM_TC_STATS
             if (a.dbg && (i & 255) == 0 && (i >> 8) < 48 && blockIdx.x + a.tile_offset == 200 && warp == 0 && lane == 0)     // tile-rate profile of one CTA
@@ -428,7 +443,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
             const uint2 tp = tnext;
             if (i + 2 < n_tiles) tnext = tsrc[(size_t)(i + 2) * TC_N];       // prefetch this thread's next target
             const uint32_t e[3] = {tp.x & ~tp.y, tp.y & ~tp.x, tp.x & tp.y};     // C, G, T (an A is three zero bytes)
-            if (round > 0 && !(GM_TC_ABL & 32)) tc_wait(&b_empty[s], (round - 1) & 1u);
+            if (round > 0 && !(GM_TC_ABL & 32)) TC_WAIT_T(0, &b_empty[s], (round - 1) & 1u);
             uint8_t *dstp = sB + (size_t)s * b_bytes + (size_t)p * 16;
 #pragma unroll
             for (int j = 0; j < ((GM_TC_ABL & 2) ? 0 : kc); j++) {  // positions beyond L have all-zero masks
@@ -460,9 +475,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
         const uint32_t d = tmem_u + (uint32_t)q * (2 * TC_N) + (uint32_t)par * TC_N;
         for (int i = par; i < n_tiles; i += 2) {
             const int s = i % TC_STAGES;
-            tc_wait(&b_full[s], (uint32_t)((i / TC_STAGES) & 1));
+            TC_WAIT_T(0, &b_full[s], (uint32_t)((i / TC_STAGES) & 1));
             if (i >= 2) {
-                tc_wait(&acc_empty[q][par], (uint32_t)(((i >> 1) - 1) & 1));
+                TC_WAIT_T(1, &acc_empty[q][par], (uint32_t)(((i >> 1) - 1) & 1));
                 // Tile i - 2 of this set has been multiplied AND read out, so the set is done with its B stage: release it
                 // here with a plain arrive.  (A second tcgen05.commit right after the MMAs would release it earlier, but a
                 // commit stalls the issuing thread until its MMAs have completed -- measured: 3 MMAs + 1 commit take 467
@@ -475,10 +490,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
             // strictly closer than the k-th best" exact under the (distance, index) order.
             if (ld_vol(&s_issued[q]) != (uint32_t)i) {
                 const long long w0 = clock64();
+#ifdef GM_TC_STATS
+                const long long w0s = w0;
+#endif
                 while (ld_vol(&s_issued[q]) != (uint32_t)i) {
                     __nanosleep(20);                                // (a tight loop would eat shared-memory cycles)
                     if (clock64() - w0 > 20000000000LL) tc_watchdog(1);
                 }
+#ifdef GM_TC_STATS
+                if (lane == 0 && a.dbg) wait_clk[2] += (unsigned long long)(clock64() - w0s);
+#endif
             }
             tc_fence_after();
             const uint64_t db = db0 + (uint64_t)((uint32_t)s * b_stage);
@@ -592,6 +613,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
         TC_STAT(if (a.dbg && lane == 0) { atomicAdd(&a.dbg[0], n_events); atomicAdd(&a.dbg[1], n_inserts); })
     }
 
+#ifdef GM_TC_STATS
+    if (a.dbg && lane == 0) {
+        const int role = warp < TC_EPI_WARPS ? 0 : warp < TC_MMA_WARP ? 1 : warp < TC_CAND_WARP0 ? 2 : 3;
+        atomicAdd(&a.dbg[64 + role * 4 + 0], wait_clk[0]);
+        atomicAdd(&a.dbg[64 + role * 4 + 1], wait_clk[1]);
+        atomicAdd(&a.dbg[64 + role * 4 + 2], wait_clk[2]);
+        atomicAdd(&a.dbg[64 + role * 4 + 3], (unsigned long long)(clock64() - role_t0));
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     if (tid < TC_QT) {                                              // publish the finished lists

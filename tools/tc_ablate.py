@@ -81,7 +81,7 @@ def run(names):
             out[name] = json.loads(line[-1][7:]) if line else {"error": (r.stdout + r.stderr)[-600:]}
             dbg = [ln for ln in r.stderr.splitlines() if ln.startswith("[tc_dbg]")]
             if dbg:
-                out[name]["dbg"] = dbg[-2:]
+                out[name]["dbg"] = dbg[-5:]
         except subprocess.TimeoutExpired:
             out[name] = {"error": "timeout"}
         print(name, out[name], flush=True)
