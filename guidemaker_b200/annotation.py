@@ -103,7 +103,7 @@ def read_genbank_features(path: str):
     of strings as in Biopython (quotes stripped, continuation lines joined with a space -- without one for
     ``translation``); a valueless qualifier (``/pseudo``) has the value ``['']``."""
     locus = accession = version = None
-    in_features, pending = False, []        # pending: features of the current record (the id may follow later? no: header first)
+    in_features = False
     cur = None                              # [type, location string, [qualifier lines]]
 
     def flush(cur):

@@ -6,7 +6,6 @@ table at once on the GPU (``gm_cfd_scores``: double precision, the reference's m
 and its ``str()`` in the 'CFD Similar Guides' column -- equals the reference's)."""
 from __future__ import annotations
 
-import ctypes
 import json
 import os
 from typing import Dict, Tuple

@@ -15,7 +15,7 @@ import pandas as pd
 import pytest
 
 from oracle import oracle as O
-from tests.conftest import ROOT, Rec, _OracleSession
+from tests.conftest import ROOT, _OracleSession
 
 pytestmark = pytest.mark.gpu
 
@@ -183,7 +183,6 @@ def _check_rows_vs_oracle(tp, L, metric, knum, n_rows, seed):
     qmask = (~t["isseedduplicated"].to_numpy()) | (~t["hasrestrictionsite"].to_numpy().astype(bool))
     sel = rows[qmask[rows]]
     keep = od[qmask[rows], 1] >= tp.editdist
-    from guidemaker_b200._encode import decode_guides
     for r, k_ in zip(sel[:200], keep[:200]):
         assert (t["target"].iat[int(r)] in tp.neighbors) == bool(k_)
     return g, uniq
