@@ -383,6 +383,7 @@ def run_ours(args):
                                    "(MEASURED_PEAKS.json has no int8 figure; its 2 x bf16 burst proxy is 3354 TOP/s)",
                     "algorithmic_ops_per_comparison": ops_alg, "executed_ops_per_comparison": ops_exec,
                     "frac_executed": achieved * ops_exec / i8_rate,
+                    "frac_in_round1_units": achieved * 96 / i8_rate,        # what the same rate would need with the 4-byte one-hot code (K = 96)
                     "encoding": "3 bytes per base (rank-minimal ternary/0-1 code), K = 64 for 20-nt guides: two 32-byte MMA K steps per tile "
                                 "(the 4-byte one-hot code of round 1 needed three)",
                     "comparisons_per_s": achieved, "kernel": "knn_hamming_tc_kernel<KC> (+ warm-up knn_hamming_scan_kernel)",
