@@ -386,7 +386,7 @@ def run_ours(args):
                     "frac_in_round1_units": achieved * 96 / i8_rate,        # what the same rate would need with the 4-byte one-hot code (K = 96)
                     "encoding": "3 bytes per base (rank-minimal ternary/0-1 code), K = 64 for 20-nt guides: two 32-byte MMA K steps per tile "
                                 "(the 4-byte one-hot code of round 1 needed three)",
-                    "comparisons_per_s": achieved, "kernel": "knn_hamming_tc_kernel<KC> (+ warm-up knn_hamming_scan_kernel)",
+                    "comparisons_per_s": achieved, "kernel": "knn_hamming_tc_kernel<KC> (+ the neighbourhood warm start: radix sort of the queries, warm_window_kernel)",
                     "kernel_ms_per_launch": scan_ms, "kernel_share_of_step": prof["scan_kernel_ms"] / ms_total,
                     "algorithmic_bytes_per_launch": alg_bytes, "hbm_equiv_gbs": alg_bytes / (scan_ms * 1e-3) / 1e9,
                     "traffic": traffic.get("knn_hamming_tc_kernel_dram_bytes_per_launch_" + args.workload)}

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libgm_b200.so")
-SOURCES = ["api.cu", "knn.cu", "knn_tc.cu", "dedup.cu", "pam_scan.cu", "restriction.cu", "session.cu", "cfd.cu", "comm.cu"]
+SOURCES = ["api.cu", "knn.cu", "knn_tc.cu", "warm.cu", "dedup.cu", "pam_scan.cu", "restriction.cu", "session.cu", "cfd.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 

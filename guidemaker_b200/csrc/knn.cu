@@ -366,6 +366,15 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     int warm = tune_warm < 0 ? (ix->metric == GM_METRIC_LEVEN ? 0 : (use_tc ? 8 : 4) * CHUNK) : tune_warm;
     warm = (warm + CHUNK - 1) / CHUNK;                       // in chunks
     if (n_chunks < 16 * warm || ix->n_u < (int64_t)warm * CHUNK) warm = 0;
+    // K3b's default is the neighbourhood warm start instead (warm.cu): a bound from the 2 x WINDOW guides around the
+    // query's rank in two sorted copies of the table; an explicit warm_sample > 0 keeps the first-chunks sample.
+    // Measured on the 6.3 Mb table (tools/warm_sweep.py, ms per pass): first 8192 guides 62.8; windows of 256 / 512 / 1024 /
+    // 2048 in one copy 60.4 / 59.6 / 59.3 / 59.4, in two copies 57.4 / 57.1 / 57.2 / 58.4, in three 56.2 / 56.4 / 57.5 / 59.5,
+    // in four 56.1 / 56.9 / 58.3 / 60.7.  GM_WARM_WINDOW / GM_WARM_COPIES override the defaults for such sweeps.
+    const char *w_env = getenv("GM_WARM_WINDOW");
+    const int WINDOW = w_env && atoi(w_env) > 0 ? atoi(w_env) : 512;
+    const bool window_warm = use_tc && tune_warm < 0 && ix->n_u >= 64 * WINDOW && q < (1LL << 31);
+    if (window_warm) warm = 0;
     // K3b inherits the warm lists and scans only the chunks behind the sample; K3a rescans from chunk 0
     const int first_chunk = use_tc ? warm : 0;
     const int scan_chunks = n_chunks - first_chunk;
@@ -390,13 +399,13 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     const size_t main_bytes = (size_t)splits * q_pad * k * sizeof(uint32_t);
     const size_t tail_bytes = (size_t)(tail_tiles ? tail_splits : 0) * tail_q * k * sizeof(uint32_t);
     const size_t list_bytes = main_bytes + tail_bytes;
-    const size_t warm_bytes = warm ? (size_t)q_pad * k * sizeof(uint32_t) : 0;
+    const size_t warm_bytes = (warm || window_warm) ? (size_t)q_pad * k * sizeof(uint32_t) : 0;
     int rc = ensure_ws(ix, qp_bytes + list_bytes + warm_bytes, st);
     if (rc) return rc;
     uint2 *qplanes = reinterpret_cast<uint2 *>(ix->ws);
     uint32_t *lists = reinterpret_cast<uint32_t *>((char *)ix->ws + qp_bytes);
     uint32_t *tlists = reinterpret_cast<uint32_t *>((char *)ix->ws + qp_bytes + main_bytes);
-    uint32_t *wlists = warm ? reinterpret_cast<uint32_t *>((char *)ix->ws + qp_bytes + list_bytes) : nullptr;
+    uint32_t *wlists = warm_bytes ? reinterpret_cast<uint32_t *>((char *)ix->ws + qp_bytes + list_bytes) : nullptr;
 
     double t_l = now_ms();
     to_planes_kernel<<<(unsigned)((q_pad + 255) / 256), 256, 0, st>>>(d_q, q, q_pad, qplanes);
@@ -417,6 +426,7 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     a.L = ix->L;
     a.list_stride = q_pad;
     a.list_q0 = 0;
+    a.warm_any_subset = window_warm ? 1 : 0;
     a.dbg = nullptr;
     unsigned long long *&d_dbg = ix->dbg;
     const char *dbg_env = getenv("GM_TC_DEBUG");
@@ -436,6 +446,11 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
         if (R == 8) launch_scan<8>(ix->metric, dim3((unsigned)tiles, 1), st, a);
         else launch_scan<4>(ix->metric, dim3((unsigned)tiles, 1), st, a);
         pairs += (double)q * (double)warm * CHUNK;
+    }
+    if (window_warm) {
+        rc = warm_window(ix, qplanes, q, k, WINDOW, wlists, st);
+        if (rc) return rc;
+        pairs += (double)q * 2.0 * WINDOW;
     }
     a.n_chunks = n_chunks;
     a.chunks_per_split = cps;
@@ -595,6 +610,7 @@ extern "C" int gm_index_free(void *index) {
     cudaDeviceSynchronize();
     dev_free(ix->planes, 0);
     dev_free(ix->planes_perm, 0);
+    warm_free_index(ix);
     park_ws(ix->ws, ix->ws_bytes);
     if (ix->dbg) cudaFree(ix->dbg);
     delete ix;

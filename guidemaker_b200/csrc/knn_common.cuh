@@ -25,6 +25,9 @@ struct Index {
     // per-handle tuning (gm_index_tune); a negative value follows the process-wide default (gm_knn_tune / gm_knn_engine)
     int engine = -1, tune_r = -1, tune_splits = -1, tune_warm = -2;
     unsigned long long *dbg = nullptr;      // GM_TC_DEBUG counters of this index
+    // warm.cu: the table sorted by guide (copy 0) and by guide with its positions rotated by L/2 (copy 1), built lazily
+    uint2 *sorted_p[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t *sorted_i[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 
@@ -68,6 +71,8 @@ struct ScanArgs {
     int64_t list_stride;      // queries per split in `lists` (q_pad, or the tail's query count for K3b's tail launch)
     int64_t list_q0;          // first query stored in `lists`
     const uint32_t *warm;     // [q_pad][k] lists of the warm-up launch or nullptr
+    int warm_any_subset;      // K3b: `warm` comes from an arbitrary subset of the table (warm.cu), not from its first chunks:
+                              // only the k-th distance is used, as an INCLUSIVE bound, and no split inherits the lists
     int L;
     unsigned long long *dbg;  // optional per-role cycle counters of block (0,0) (GM_TC_DEBUG=1), else nullptr
 };
@@ -84,5 +89,8 @@ int tc_permute_planes(const uint2 *planes, int64_t n, uint2 *out, cudaStream_t s
 int tc_query_tile();
 int tc_k_chunks(int L);
 int microbench_mma_i8(int variant, double *ops_per_s);
+// neighbourhood warm start (warm.cu)
+int warm_window(Index *ix, const uint2 *qplanes, int64_t q, int k, int W, uint32_t *wlists, cudaStream_t st);
+void warm_free_index(Index *ix);
 
 }  // namespace gm

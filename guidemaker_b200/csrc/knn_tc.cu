@@ -293,7 +293,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
         if (a.warm) {
             const uint32_t *w = a.warm + (size_t)qi * a.k;
             const uint32_t wk = w[a.k - 1];
-            if (blockIdx.y == 0) {
+            if (a.warm_any_subset) {
+                // the warm entries may sit anywhere in the table: start empty and let every guide at a distance <= w0
+                // through (at least k of them exist, so the list fills and the usual tightening takes over)
+                for (int j = 0; j < a.k; j++) lst[j * TC_QT] = KEY_EMPTY;
+                bound = wk == KEY_EMPTY ? KEY_EMPTY : ((wk >> IDX_BITS) + 1u) << IDX_BITS;
+            } else if (blockIdx.y == 0) {
                 for (int j = 0; j < a.k; j++) lst[j * TC_QT] = w[j];
                 bound = wk;
             } else {

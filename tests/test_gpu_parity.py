@@ -293,6 +293,31 @@ def test_knn_tc_tail_wave_launch(capi_mod):
     assert np.array_equal(d1, b[1][-5000:, 0])
 
 
+@pytest.mark.parametrize("L,k,splits", [(9, 1, 0), (9, 5, 0), (11, 32, 0), (20, 5, 5), (27, 3, 2), (2, 4, 0)])
+def test_knn_tc_neighbourhood_warm_start(tc_engine, L, k, splits):
+    """tables large enough for K3b's default warm start (warm.cu: bounds from the guides around the query's rank in two
+    sorted copies of the table), short guides so that ties at the k-th distance are everywhere; dense queries take the
+    shared-memory staging path, sparse ones read their windows from L2; also under explicit target splits"""
+    rng = np.random.default_rng(900 + L)
+    if 4 ** L < 400000:
+        t = rng.permutation(4 ** L).astype(np.uint64)[: min(4 ** L, 120000)]
+        if len(t) < 40000:                                  # L = 2: too small for the window path, must still be exact
+            t = rng.permutation(t)
+    else:
+        t, _ = O.unique_first_order(rand_guides(rng, 120000, L, n_base=100000))
+    tc_engine.knn_tune(8, splits, -1)
+    for q in (np.concatenate([t[:20000], rand_guides(rng, 20000, L)]), rand_guides(rng, 500, L)):
+        ix = tc_engine.Index(t, L, 0)
+        idx, dist = ix.knn(q, k)
+        rows = rng.integers(0, len(q), size=min(len(q), 400))
+        oi, od = O.c_knn(t, q[rows], L, 0, k)
+        assert np.array_equal(idx[rows], oi) and np.array_equal(dist[rows], od)
+        ix.tune(engine=0)                                   # all rows against the other engine
+        ref = ix.knn(q, k)
+        assert np.array_equal(idx, ref[0]) and np.array_equal(dist, ref[1])
+        ix.close()
+
+
 # ---- K6 ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("L", [1, 7, 10, 20, 27])
 def test_restriction_scan_vs_oracle(capi_mod, L):
