@@ -366,13 +366,17 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     int warm = tune_warm < 0 ? (ix->metric == GM_METRIC_LEVEN ? 0 : (use_tc ? 8 : 4) * CHUNK) : tune_warm;
     warm = (warm + CHUNK - 1) / CHUNK;                       // in chunks
     if (n_chunks < 16 * warm || ix->n_u < (int64_t)warm * CHUNK) warm = 0;
-    // K3b's default is the neighbourhood warm start instead (warm.cu): a bound from the 2 x WINDOW guides around the
-    // query's rank in two sorted copies of the table; an explicit warm_sample > 0 keeps the first-chunks sample.
-    // Measured on the 6.3 Mb table (tools/warm_sweep.py, ms per pass): first 8192 guides 62.8; windows of 256 / 512 / 1024 /
-    // 2048 in one copy 60.4 / 59.6 / 59.3 / 59.4, in two copies 57.4 / 57.1 / 57.2 / 58.4, in three 56.2 / 56.4 / 57.5 / 59.5,
-    // in four 56.1 / 56.9 / 58.3 / 60.7.  GM_WARM_WINDOW / GM_WARM_COPIES override the defaults for such sweeps.
+    // K3b's default is the neighbourhood warm start instead (warm.cu): a bound from the WINDOW guides around the query's
+    // rank in each of three sorted copies of the table; an explicit warm_sample > 0 keeps the first-chunks sample.
+    // Measured on the 6.3 Mb table (tools/warm_sweep.py, ms per pass; first 8192 guides: 62.9, no warm start: 113.4):
+    //   window   256    512    1024   2048
+    //   1 copy   57.5   56.7   56.0   55.8
+    //   2        54.4   54.0   53.7   54.6
+    //   3        52.9   53.0   53.9   55.6
+    //   4        52.7   53.4   54.5   56.9
+    // GM_WARM_WINDOW / GM_WARM_COPIES override the defaults for such sweeps.
     const char *w_env = getenv("GM_WARM_WINDOW");
-    const int WINDOW = w_env && atoi(w_env) > 0 ? atoi(w_env) : 512;
+    const int WINDOW = w_env && atoi(w_env) > 0 ? atoi(w_env) : 256;
     const bool window_warm = use_tc && tune_warm < 0 && ix->n_u >= 64 * WINDOW && q < (1LL << 31);
     if (window_warm) warm = 0;
     // K3b inherits the warm lists and scans only the chunks behind the sample; K3a rescans from chunk 0
@@ -450,7 +454,7 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     if (window_warm) {
         rc = warm_window(ix, qplanes, q, k, WINDOW, wlists, st);
         if (rc) return rc;
-        pairs += (double)q * 2.0 * WINDOW;
+        pairs += (double)q * warm_copies() * WINDOW;
     }
     a.n_chunks = n_chunks;
     a.chunks_per_split = cps;
@@ -491,7 +495,7 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
                     fprintf(stderr, "\n");
                 }
             }
-            fprintf(stderr, "[tc_dbg] cycles per tile over successive 256-tile windows of CTA 200:");
+            fprintf(stderr, "[tc_dbg] cycles per tile over successive 256-tile windows of one CTA:");
             for (int w = 1; w < 48 && h[8 + w]; w++) fprintf(stderr, " %.0f", (double)(h[8 + w] - h[8 + w - 1]) / 256.0);
             fprintf(stderr, "\n");
         }

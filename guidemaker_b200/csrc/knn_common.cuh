@@ -25,7 +25,7 @@ struct Index {
     // per-handle tuning (gm_index_tune); a negative value follows the process-wide default (gm_knn_tune / gm_knn_engine)
     int engine = -1, tune_r = -1, tune_splits = -1, tune_warm = -2;
     unsigned long long *dbg = nullptr;      // GM_TC_DEBUG counters of this index
-    // warm.cu: the table sorted by guide (copy 0) and by guide with its positions rotated by L/2 (copy 1), built lazily
+    // warm.cu: copies of the table sorted by guide with its positions rotated by c * L / copies, built lazily
     uint2 *sorted_p[4] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t *sorted_i[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -92,5 +92,6 @@ int microbench_mma_i8(int variant, double *ops_per_s);
 // neighbourhood warm start (warm.cu)
 int warm_window(Index *ix, const uint2 *qplanes, int64_t q, int k, int W, uint32_t *wlists, cudaStream_t st);
 void warm_free_index(Index *ix);
+int warm_copies();
 
 }  // namespace gm

@@ -71,6 +71,9 @@ static constexpr int TC_SETS = 2;          // A operands (query tiles) per CTA
 #ifndef GM_TC_TOKEN_FENCE
 #define GM_TC_TOKEN_FENCE 0
 #endif
+#ifndef GM_TC_STATS_CTA
+#define GM_TC_STATS_CTA 200                 // the CTA whose tile-rate profile -DGM_TC_STATS records
+#endif
 #ifndef GM_TC_STAGES
 #define GM_TC_STAGES 6
 #endif
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_hamming_tc_kernel(const Sca
             TC_WAIT_T(0, &acc_full[set][par], (uint32_t)((i >> 1) & 1));
             tc_fence_after();
 #ifdef GM_TC_STATS
-            if (a.dbg && (i & 255) == 0 && (i >> 8) < 48 && blockIdx.x + a.tile_offset == 200 && warp == 0 && lane == 0)     // tile-rate profile of one CTA
+            if (a.dbg && (i & 255) == 0 && (i >> 8) < 48 && blockIdx.x + a.tile_offset == GM_TC_STATS_CTA && warp == 0 && lane == 0)     // tile-rate profile of one CTA
                 a.dbg[8 + (i >> 8)] = (unsigned long long)(clock64() - t_begin);
 #endif
             uint32_t f[4];

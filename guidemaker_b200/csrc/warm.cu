@@ -4,11 +4,11 @@
 // over ANY k distinct guides of the table is an upper bound of the query's final k-th distance.  The tighter it is, the
 // fewer candidates the tensor-core filter flags while the lists are still loose (the start-up phase of K3b: 12 % of a
 // CTA's life on the 6.3 Mb table with a bound taken from the first 8192 guides).  Guides that share a long run of bases
-// with the query are much better than a random sample, and sorting finds them: the index keeps two copies of the table
-// sorted by the guide read as a base-4 number, once as it is and once with its positions rotated by L/2, so a query's
-// neighbours in the first copy share its last bases and in the second its first bases.  Per query batch: sort the
+// with the query are much better than a random sample, and sorting finds them: the index keeps three copies of the table
+// sorted by the guide read as a base-4 number, with its positions rotated by 0, L/3 and 2L/3, so a query's neighbours in
+// copy c share the run of bases that ends at the rotation point.  Per query batch and copy: sort the
 // queries the same way (radix sort of 2L-bit keys), locate every query in the sorted table (binary search) and scan the
-// W guides around that rank.  Queries that are adjacent in sorted order have overlapping windows, so a CTA of 256
+// W guides around that rank, keeping the k best of all copies (without duplicates) in shared memory.  Queries that are adjacent in sorted order have overlapping windows, so a CTA of 256
 // queries stages the union of its windows in shared memory once.  The result is an ordinary [q][k] list of
 // (distance << 27 | guide index) keys; only the distance of its last entry is used (knn_tc.cu: inclusive bound).
 //
@@ -22,7 +22,7 @@ namespace gm {
 
 static constexpr int WARM_THREADS = 256;
 static constexpr int WARM_CAP = 3072;           // guides a CTA can stage: 36 KB of shared memory
-static int warm_copies() { const char *e = getenv("GM_WARM_COPIES"); const int c = e ? atoi(e) : 2; return c < 1 ? 1 : c > 4 ? 4 : c; }
+int warm_copies() { const char *e = getenv("GM_WARM_COPIES"); const int c = e ? atoi(e) : 3; return c < 1 ? 1 : c > 4 ? 4 : c; }
 
 // positions rotated right by h within the L-bit planes (a common permutation of the positions keeps Hamming distances)
 __device__ __forceinline__ uint2 warm_rot(uint2 p, int h, int L) {
@@ -46,26 +46,32 @@ __global__ void warm_gather_kernel(const uint2 *__restrict__ planes, const uint3
     if (i < n) out[i] = warm_rot(planes[ids[i]], h, L);
 }
 
-// Insert `key` unless the list already holds it (the two sorted copies show a query some guides twice).  Returns the
-// distance bound for the next test: insert candidates have distance <= bound.
-static __device__ __noinline__ uint32_t warm_insert(uint32_t *__restrict__ lst, int k, uint32_t key) {
-    if (key < lst[k - 1]) {
+// Insert `key` into the thread's list (shared memory, stride WARM_THREADS between ranks) unless the list already holds it
+// (the sorted copies show a query some guides twice).  Returns the distance bound for the next test: insert candidates
+// have distance <= bound.
+static __device__ __forceinline__ uint32_t warm_insert(uint32_t *lst, int k, uint32_t key) {
+    if (key < lst[(k - 1) * WARM_THREADS]) {
         int pos = k - 1;
-        while (pos > 0 && lst[pos - 1] > key) pos--;
-        if (pos == 0 || lst[pos - 1] != key) {
-            for (int j = k - 1; j > pos; j--) lst[j] = lst[j - 1];
-            lst[pos] = key;
+        while (pos > 0 && lst[(pos - 1) * WARM_THREADS] > key) pos--;
+        if (pos == 0 || lst[(pos - 1) * WARM_THREADS] != key) {
+            for (int j = k - 1; j > pos; j--) lst[j * WARM_THREADS] = lst[(j - 1) * WARM_THREADS];
+            lst[pos * WARM_THREADS] = key;
         }
     }
-    const uint32_t worst = lst[k - 1];
+    const uint32_t worst = lst[(k - 1) * WARM_THREADS];
     return worst == KEY_EMPTY ? 32u : worst >> IDX_BITS;
 }
+
+// dynamic shared memory: WARM_CAP staged guides (planes, indices) + the CTA's lists [k][WARM_THREADS]
+static size_t warm_smem_bytes(int k) { return (size_t)WARM_CAP * 12 + (size_t)k * WARM_THREADS * 4; }
 
 __global__ void __launch_bounds__(WARM_THREADS) warm_window_kernel(const uint2 *__restrict__ sp, const uint32_t *__restrict__ si, int n,
                                                                    const uint2 *__restrict__ qplanes, const uint32_t *__restrict__ sq,
                                                                    int64_t q, int k, int W, int h, int L, uint32_t *__restrict__ wlists) {
-    __shared__ uint2 s_p[WARM_CAP];
-    __shared__ uint32_t s_i[WARM_CAP];
+    extern __shared__ __align__(16) uint8_t warm_smem[];
+    uint2 *s_p = reinterpret_cast<uint2 *>(warm_smem);
+    uint32_t *s_i = reinterpret_cast<uint32_t *>(s_p + WARM_CAP);
+    uint32_t *s_l = s_i + WARM_CAP;
     __shared__ int s_lo, s_hi;
     const int tid = threadIdx.x;
     const int64_t i = (int64_t)blockIdx.x * WARM_THREADS + tid;
@@ -75,9 +81,11 @@ __global__ void __launch_bounds__(WARM_THREADS) warm_window_kernel(const uint2 *
     uint32_t qi = 0;
     uint2 p = make_uint2(0u, 0u);
     int lo = 0, hi = 0;
+    uint32_t *lst = s_l + tid;
     if (active) {
         qi = sq[i];
         p = warm_rot(qplanes[qi], h, L);
+        for (int j = 0; j < k; j++) lst[j * WARM_THREADS] = wlists[(size_t)qi * k + j];     // the previous copy's result
         const uint64_t key = from_planes(p.x, p.y);
         int a = 0, b = n;                                         // first guide whose key is >= the query's
         while (a < b) {
@@ -98,22 +106,24 @@ __global__ void __launch_bounds__(WARM_THREADS) warm_window_kernel(const uint2 *
         __syncthreads();
     }
     if (!active) return;
-    uint32_t *lst = wlists + (size_t)qi * k;
-    const uint32_t w0 = lst[k - 1];
+    const uint32_t w0 = lst[(k - 1) * WARM_THREADS];
     uint32_t bound = w0 == KEY_EMPTY ? 32u : w0 >> IDX_BITS;
     if (staged) {
+#pragma unroll 4
         for (int j = lo - base; j < hi - base; j++) {
             const uint2 t = s_p[j];
             const uint32_t d = (uint32_t)hamming_planes(p.x, p.y, t.x, t.y);
             if (d <= bound) bound = warm_insert(lst, k, (d << IDX_BITS) | s_i[j]);
         }
     } else {                                                      // sparse queries: every window straight from L2
+#pragma unroll 4
         for (int j = lo; j < hi; j++) {
             const uint2 t = sp[j];
             const uint32_t d = (uint32_t)hamming_planes(p.x, p.y, t.x, t.y);
             if (d <= bound) bound = warm_insert(lst, k, (d << IDX_BITS) | si[j]);
         }
     }
+    for (int j = 0; j < k; j++) wlists[(size_t)qi * k + j] = lst[j * WARM_THREADS];
 }
 
 // keys -> ids in key order (ids_out), by radix sort over the 2L significant bits
@@ -172,10 +182,15 @@ void warm_free_index(Index *ix) {
     }
 }
 
-// wlists ([q_pad][k], preset to KEY_EMPTY) <- k best of the 2 x W guides around every query's rank in the sorted copies
+// wlists ([q_pad][k], preset to KEY_EMPTY) <- k best of the copies x W guides around every query's rank in the sorted copies
 int warm_window(Index *ix, const uint2 *qplanes, int64_t q, int k, int W, uint32_t *wlists, cudaStream_t st) {
     int rc = warm_build_index(ix, st);
     if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GM_CUDA(cudaFuncSetAttribute(warm_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warm_smem_bytes(GM_MAX_K)));
+        attr_set = true;
+    }
     uint32_t *sq = nullptr;
     GM_CUDA(dev_alloc((void **)&sq, (size_t)q * 4, st));
     const int C = warm_copies();
@@ -183,7 +198,7 @@ int warm_window(Index *ix, const uint2 *qplanes, int64_t q, int k, int W, uint32
         const int h = c * ix->L / C;
         rc = warm_sort(qplanes, q, h, ix->L, sq, st);
         if (rc) break;
-        warm_window_kernel<<<(unsigned)((q + WARM_THREADS - 1) / WARM_THREADS), WARM_THREADS, 0, st>>>(
+        warm_window_kernel<<<(unsigned)((q + WARM_THREADS - 1) / WARM_THREADS), WARM_THREADS, warm_smem_bytes(k), st>>>(
             ix->sorted_p[c], ix->sorted_i[c], (int)ix->n_u, qplanes, sq, q, k, W, h, ix->L, wlists);
         count_launch();
     }

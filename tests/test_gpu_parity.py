@@ -295,7 +295,7 @@ def test_knn_tc_tail_wave_launch(capi_mod):
 
 @pytest.mark.parametrize("L,k,splits", [(9, 1, 0), (9, 5, 0), (11, 32, 0), (20, 5, 5), (27, 3, 2), (2, 4, 0)])
 def test_knn_tc_neighbourhood_warm_start(tc_engine, L, k, splits):
-    """tables large enough for K3b's default warm start (warm.cu: bounds from the guides around the query's rank in two
+    """tables large enough for K3b's default warm start (warm.cu: bounds from the guides around the query's rank in
     sorted copies of the table), short guides so that ties at the k-th distance are everywhere; dense queries take the
     shared-memory staging path, sparse ones read their windows from L2; also under explicit target splits"""
     rng = np.random.default_rng(900 + L)

@@ -1,4 +1,4 @@
-"""A/B of K3b's warm start on the GPU: neighbourhood windows in two sorted copies of the table (default) against the
+"""A/B of K3b's warm start on the GPU: neighbourhood windows in sorted copies of the table (default) against the
 first-8192-guides sample and against no warm start; results must be identical.  `python tools/warm_ab.py [workload]`"""
 import os
 import sys
@@ -34,7 +34,7 @@ def run(ix, q, k, reps):
 
 ix = _capi.Index(uniq, 20, 0)
 ref = None
-for label, warm in (("window 2 x 1024 (default)", -1), ("first 8192 guides", 8192), ("none", 0), ("window again", -1)):
+for label, warm in (("neighbourhood windows (default)", -1), ("first 8192 guides", 8192), ("none", 0), ("window again", -1)):
     ix.tune(engine=1, warm_sample=warm)
     (idx, dist), ms = run(ix, g, 5, 3)
     same = "" if ref is None else ("same" if np.array_equal(idx, ref[0]) and np.array_equal(dist, ref[1]) else "DIFFERENT")
