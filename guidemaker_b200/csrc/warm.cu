@@ -141,7 +141,7 @@ static int warm_sort(const uint2 *planes, int64_t n, int h, int L, uint32_t *ids
         warm_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(planes, n, h, L, k_in, v_in);
         count_launch();
         e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, ids_out, (int)n, 0, 2 * L, st);
-        count_launch(4);
+        count_launch(2 + (2 * L + 7) / 8);                       // histogram, exclusive sum, one onesweep pass per 8 key bits
     }
     dev_free(k_in, st); dev_free(k_out, st); dev_free(v_in, st); dev_free(tmp, st);     // stream ordered
     if (e != cudaSuccess) return cuda_fail(e, "warm_sort", __FILE__, __LINE__);
