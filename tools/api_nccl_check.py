@@ -56,4 +56,5 @@ dist.barrier()
 dist.destroy_process_group()
 if not ok:
     raise SystemExit(1)
-print("API_NCCL_OK", rank)
+sys.stdout.write("API_NCCL_OK %d\n" % rank)      # one write: the ranks share the pipe
+sys.stdout.flush()
