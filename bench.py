@@ -480,20 +480,32 @@ def run_ours(args):
                              "comparisons_per_s_per_gpu": rate_o, "kernel_ms": p_o["scan_kernel_ms"],
                              "frac_of_popc_peak": rate_o / popc_rate if other == 0 else None, "popc_peak_lane_ops_per_s": popc_rate}}
         r2.close()
-        # K4: Levenshtein on the same table, a bounded slice of the query rows (the kernel is ~300x slower per pair)
+        # K4: Levenshtein on the same table, a bounded slice of the query rows (the kernel is ~200x slower per pair):
+        # the prefix-sharing scan (K4p, default) and the plain scan (engine 0) beside it; same bits
         nq = min(len(g2), 65536 * world)
         r4 = Resident(g2[:nq], u2, metric=1)
         r4.step(); torch.cuda.synchronize()
         ms4, p4 = timed(r4, 1)
+        out4 = r4.full_result()
+        r4.ix.tune(engine=0)
+        r4.step(); torch.cuda.synchronize()
+        ms4p, p4p = timed(r4, 1)
+        same4 = all(np.array_equal(x, y) for x, y in zip(out4, r4.full_result()))
         lop_rate = _capi.microbench(1)
         rate4 = p4["pairs"] / (p4["scan_kernel_ms"] * 1e-3)
-        leven = {"metric": "Levenshtein comparisons/s (20-nt, Myers bit-parallel, K4)", "value": float(nq) * len(u2) / (ms4 * 1e-3),
+        rate4p = p4p["pairs"] / (p4p["scan_kernel_ms"] * 1e-3)
+        leven = {"metric": "Levenshtein comparisons/s (20-nt, Myers bit-parallel, K4p: prefix-sorted table, shared DP states)",
+                 "value": float(nq) * len(u2) / (ms4 * 1e-3),
                  "kernel_comparisons_per_s_per_gpu": rate4, "queries": int(nq), "indexed_guides": int(len(u2)),
                  "cell_updates_per_s_per_gpu": rate4 * GUIDE_LEN * GUIDE_LEN,
                  "lop3_peak_lane_ops_per_s": lop_rate, "alu_ops_per_comparison": 7 * GUIDE_LEN,
                  "frac_of_alu_peak": rate4 * 7 * GUIDE_LEN / lop_rate,
+                 "plain_kernel": {"kernel_comparisons_per_s_per_gpu": rate4p, "frac_of_alu_peak": rate4p * 7 * GUIDE_LEN / lop_rate,
+                                  "same_output": bool(same4)},
                  "note": "7 LOP3 (ALU pipe) + 3 IMAD (FMA pipe) per pair and text step, counted in the SASS; peak = LOP3 lane rate measured "
-                         "live (gm_microbench(1)); ncu on the same launch: ALU pipe 84 % (profiles/r02_ncu_full_knn_leven_scan.csv)"}
+                         "live (gm_microbench(1)); alu_ops_per_comparison = 7 L is the ALGORITHMIC count of the plain recurrence (ncu: ALU "
+                         "pipe 84 %, profiles/r02_ncu_full_knn_leven_scan.csv) -- K4p executes ~L - log4(n) of the L steps per pair, so its "
+                         "fraction can exceed 1"}
         r4.close()
 
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------

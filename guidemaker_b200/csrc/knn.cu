@@ -236,6 +236,148 @@ __global__ void __launch_bounds__(THREADS) knn_leven_scan_kernel(const ScanArgs 
         if (++stage == NSTAGE) { stage = 0; parity ^= 1u; }
     }
 }
+
+// ---- K4p: Levenshtein pair scan over the PREFIX-SORTED table ---------------------------------------------------------
+// Myers' recurrence consumes the text (the target) base by base and its state after j bases -- (Pv, Mv) per query --
+// depends only on the text's first j bases.  The index keeps a copy of the table sorted by the guides read from their
+// first base (warm.cu: sorted_by_prefix); consecutive guides of that copy share their first ~log4(n) bases (10 of 20 for
+// 1.4 M guides), and the target is warp- and CTA-uniform, so the states of the previous target after c0 .. c0+NL-1 bases
+// are kept in shared memory ([level][2R][thread], 8 KB per level at R = 8) and a target resumes from the deepest kept
+// level its common prefix with its predecessor reaches: ~L - log4(n) steps per pair instead of L.  Targets no longer
+// arrive in index order, so the lists work on full (distance, original index) keys: a tie at the k-th distance gets in
+// iff its index is lower.  Same bits as the plain kernel.
+#ifndef GM_PFX_LEVELS
+#define GM_PFX_LEVELS 2
+#endif
+static constexpr int PFX_LEVELS = GM_PFX_LEVELS;
+static constexpr int PFX_STAGES = 2;
+static size_t pfx_smem_bytes(int R) { return (size_t)PFX_STAGES * CHUNK * 12 + (size_t)PFX_LEVELS * 2 * R * THREADS * 4; }
+
+// insert by full key; returns the key of the (new) worst entry, KEY_EMPTY while the list is not full
+static __device__ __noinline__ uint32_t list_insert_key(uint32_t *__restrict__ lst, int k, uint32_t key) {
+    uint32_t worst = lst[k - 1];
+    if (key < worst) {
+        int pos = k - 1;
+        while (pos > 0) {
+            uint32_t v = lst[pos - 1];
+            if (v <= key) break;
+            lst[pos] = v;
+            pos--;
+        }
+        lst[pos] = key;
+        worst = lst[k - 1];
+    }
+    return worst;
+}
+
+template <int R>
+__global__ void __launch_bounds__(THREADS) knn_leven_prefix_kernel(const ScanArgs a) {
+    extern __shared__ __align__(128) uint8_t pfx_smem[];
+    uint2 *s_t = reinterpret_cast<uint2 *>(pfx_smem);                               // [PFX_STAGES][CHUNK] planes
+    uint32_t *s_i = reinterpret_cast<uint32_t *>(s_t + PFX_STAGES * CHUNK);         // [PFX_STAGES][CHUNK] original indices
+    uint32_t *s_stack = s_i + PFX_STAGES * CHUNK;                                   // [PFX_LEVELS][2R][THREADS]
+    __shared__ __align__(8) uint64_t s_full[PFX_STAGES];
+
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.y * a.chunks_per_split;
+    const int c1 = min(c0 + a.chunks_per_split, a.n_chunks);
+    if (c0 >= c1) return;
+
+    const int L = a.L;
+    const uint32_t lmask = (1u << L) - 1u;
+    const uint32_t two = 2u + ((uint32_t)L >> 30);          // opaque 2: keeps the shifts on the FMA pipe (see K4)
+    const int lv0 = a.prefix_c0, lv_top = a.prefix_c0 + PFX_LEVELS - 1;             // kept levels: lv0 .. lv_top (< L)
+    const int64_t qbase = (int64_t)blockIdx.x * (THREADS * R) + tid;
+    uint32_t pmA[R], pmC[R], pmG[R], pmT[R], bound[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int64_t qi = qbase + (int64_t)r * THREADS;
+        const uint2 p = a.qplanes[qi];
+        pmA[r] = ~(p.x | p.y);
+        pmC[r] = p.x & ~p.y;
+        pmG[r] = p.y & ~p.x;
+        pmT[r] = p.x & p.y;
+        uint32_t b = KEY_EMPTY;                             // insert iff key < bound
+        if (a.warm) {
+            const uint32_t w = a.warm[(size_t)qi * a.k + (a.k - 1)];
+            if (w != KEY_EMPTY) b = ((w >> IDX_BITS) + 1u) << IDX_BITS;            // everything up to the warm k-th distance
+        }
+        bound[r] = qi < a.q ? b : 0u;
+    }
+    uint32_t *const my_lists = a.lists + ((size_t)blockIdx.y * a.list_stride + (qbase - a.list_q0)) * a.k;
+
+    if (tid == 0) {
+        for (int s = 0; s < PFX_STAGES; s++) mbar_init(&s_full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int stage, int c) {
+        mbar_expect_tx(&s_full[stage], CHUNK * 12u);
+        bulk_g2s(s_t + stage * CHUNK, a.tplanes + (size_t)c * CHUNK, CHUNK * 8u, &s_full[stage]);
+        bulk_g2s(s_i + stage * CHUNK, a.tidx + (size_t)c * CHUNK, CHUNK * 4u, &s_full[stage]);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < PFX_STAGES && c0 + s < c1; s++) issue(s, c0 + s);
+    }
+
+    int stage = 0;
+    uint32_t parity = 0;
+    uint2 prev = make_uint2(0u, 0u);
+    bool have_prev = false;
+    for (int c = c0; c < c1; c++) {
+        mbar_wait(&s_full[stage], parity);
+        const uint32_t tbase = (uint32_t)c * CHUNK;
+        const int n_here = (int)min((int64_t)CHUNK, a.n_u - (int64_t)tbase);       // skip padding targets
+
+        for (int g = 0; g < n_here; g++) {
+            const uint2 t = s_t[stage * CHUNK + g];         // CTA-uniform target
+            const uint32_t oidx = s_i[stage * CHUNK + g];
+            // common prefix with the previous target, in bases (bit j of the planes = base j of the text)
+            int pl = 0;
+            if (have_prev) pl = min(__ffs((int)(((t.x ^ prev.x) | (t.y ^ prev.y)) | (1u << L))) - 1, lv_top);
+            if (pl < lv0) pl = 0;
+            prev = t;
+            have_prev = true;
+            uint32_t Pv[R], Mv[R];
+            if (pl == 0) {
+#pragma unroll
+                for (int r = 0; r < R; r++) { Pv[r] = 0xFFFFFFFFu; Mv[r] = 0u; }
+            } else {
+                const uint32_t *s = s_stack + (size_t)(pl - lv0) * (2 * R * THREADS) + tid;
+#pragma unroll
+                for (int r = 0; r < R; r++) { Pv[r] = s[(2 * r) * THREADS]; Mv[r] = s[(2 * r + 1) * THREADS]; }
+            }
+            uint64_t code = (spread_bits(t.x) | (spread_bits(t.y) << 1)) >> (2 * pl);
+#pragma unroll 1
+            for (int j = pl; j < L; j++) {
+                const uint32_t base = (uint32_t)code & 3u;   // the same in every lane: the switch is a uniform branch
+                code >>= 2;
+                if (base == 0u) { GM_MYERS_STEP(pmA) }
+                else if (base == 1u) { GM_MYERS_STEP(pmC) }
+                else if (base == 2u) { GM_MYERS_STEP(pmG) }
+                else { GM_MYERS_STEP(pmT) }
+                if (j + 1 >= lv0 && j + 1 <= lv_top) {      // state after j + 1 bases: keep it for the next targets
+                    uint32_t *s = s_stack + (size_t)(j + 1 - lv0) * (2 * R * THREADS) + tid;
+#pragma unroll
+                    for (int r = 0; r < R; r++) { s[(2 * r) * THREADS] = Pv[r]; s[(2 * r + 1) * THREADS] = Mv[r]; }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const uint32_t d = (uint32_t)(L + __popc(Pv[r] & lmask) - __popc(Mv[r] & lmask));
+                const uint32_t key = (d << IDX_BITS) | oidx;
+                if (key < bound[r]) {
+                    const uint32_t w = list_insert_key(my_lists + (size_t)r * THREADS * a.k, a.k, key);
+                    bound[r] = min(bound[r], w);
+                }
+            }
+        }
+
+        __syncthreads();
+        if (tid == 0 && c + PFX_STAGES < c1) issue(stage, c + PFX_STAGES);
+        if (++stage == PFX_STAGES) { stage = 0; parity ^= 1u; }
+    }
+}
 #undef GM_MYERS_STEP
 
 // ---- merge: k smallest keys over the splits of each query ------------------------------------------------
@@ -316,6 +458,18 @@ static void launch_scan(int metric, dim3 grid, cudaStream_t st, const ScanArgs &
     count_launch();
 }
 
+template <int R>
+static int launch_leven_prefix(dim3 grid, cudaStream_t st, const ScanArgs &a) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        GM_CUDA(cudaFuncSetAttribute(knn_leven_prefix_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pfx_smem_bytes(R)));
+        attr_set = true;
+    }
+    knn_leven_prefix_kernel<R><<<grid, THREADS, pfx_smem_bytes(R), st>>>(a);
+    count_launch();
+    return GM_OK;
+}
+
 static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_idx, uint8_t *d_dist, int dist_only,
                    cudaStream_t st) {
     GM_ARG(ix && ix->planes, "gm_knn: invalid index handle");
@@ -330,6 +484,10 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     const int tune_warm = ix->tune_warm >= -1 ? ix->tune_warm : g_tune_warm;
     const int R = tune_r == 4 ? 4 : 8;
     const bool use_tc = (ix->engine >= 0 ? ix->engine : g_tune_engine) == 1 && ix->metric == GM_METRIC_HAMMING;
+    // Levenshtein: the prefix-sharing scan over the sorted copy (K4p) unless the handle asks for the plain kernel
+    // (engine 0) or the table is too small / the guides too short for shared prefixes to exist
+    const bool use_prefix = ix->metric == GM_METRIC_LEVEN && (ix->engine >= 0 ? ix->engine : g_tune_engine) == 1 &&
+                            ix->n_u >= 4096 && ix->L >= 2 * PFX_LEVELS;
     const int QT = THREADS * R;
     const int64_t tiles = (q + QT - 1) / QT;
     const int64_t q_pad = tiles * QT;
@@ -359,6 +517,7 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
         const int64_t grid_x = use_tc ? q_pad / tc_query_tile() : tiles;
         const int64_t want = (int64_t)device_sm_count() * (use_tc ? 2 : 16);
         splits = (int)((want + grid_x - 1) / grid_x);
+        // (choosing the split count so that the CTAs fill whole waves was measured for K4 / K4p: no gain, 594 vs 582 ms)
     }
     // warm start: worthwhile only when the table is much larger than the sample
     // measured: 8192 is best for K3b, 4096 for K3a; K4 (Levenshtein) runs 1 % faster WITHOUT a warm-up launch (its warm
@@ -431,6 +590,8 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
     a.list_stride = q_pad;
     a.list_q0 = 0;
     a.warm_any_subset = window_warm ? 1 : 0;
+    a.tidx = nullptr;
+    a.prefix_c0 = 0;
     a.dbg = nullptr;
     unsigned long long *&d_dbg = ix->dbg;
     const char *dbg_env = getenv("GM_TC_DEBUG");
@@ -499,6 +660,20 @@ static int knn_run(Index *ix, const uint64_t *d_q, int64_t q, int k, int32_t *d_
             for (int w = 1; w < 48 && h[8 + w]; w++) fprintf(stderr, " %.0f", (double)(h[8 + w] - h[8 + w - 1]) / 256.0);
             fprintf(stderr, "\n");
         }
+    } else if (use_prefix) {
+        rc = sorted_by_prefix(ix, st);
+        if (rc) return rc;
+        a.tplanes = ix->prefix_p;
+        a.tidx = ix->prefix_i;
+        // keep the states after c0 .. c0 + PFX_LEVELS - 1 bases, c0 = floor(log4 n) - 1: a sorted neighbour shares at least
+        // c0 bases with probability > 0.98 (n / 4^c0 >= 4 guides per prefix)
+        int lg = 0;
+        while ((ix->n_u >> (2 * (lg + 1))) > 0) lg++;
+        a.prefix_c0 = lg - 1 < 1 ? 1 : lg - 1;
+        if (a.prefix_c0 + PFX_LEVELS > ix->L) a.prefix_c0 = ix->L - PFX_LEVELS;
+        rc = R == 8 ? launch_leven_prefix<8>(dim3((unsigned)tiles, (unsigned)splits), st, a)
+                    : launch_leven_prefix<4>(dim3((unsigned)tiles, (unsigned)splits), st, a);
+        if (rc) return rc;
     } else if (R == 8) launch_scan<8>(ix->metric, dim3((unsigned)tiles, (unsigned)splits), st, a);
     else launch_scan<4>(ix->metric, dim3((unsigned)tiles, (unsigned)splits), st, a);
     pairs += (double)q * ((double)ix->n_u - (double)first_chunk * CHUNK);

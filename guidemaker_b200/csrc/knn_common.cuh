@@ -28,6 +28,9 @@ struct Index {
     // warm.cu: copies of the table sorted by guide with its positions rotated by c * L / copies, built lazily
     uint2 *sorted_p[4] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t *sorted_i[4] = {nullptr, nullptr, nullptr, nullptr};
+    // warm.cu: Levenshtein only -- the table sorted by the guides read from their first base (K4p), padded like `planes`
+    uint2 *prefix_p = nullptr;
+    uint32_t *prefix_i = nullptr;
 };
 
 
@@ -59,6 +62,8 @@ __device__ __forceinline__ uint32_t bias_of(uint32_t tau) { return 0x7F7F7F7Fu +
 struct ScanArgs {
     const uint2 *tplanes;
     const uint2 *tperm;       // K3b: bit-permuted planes of the same table
+    const uint32_t *tidx;     // K4p: original index of every row of the prefix-sorted table `tplanes` points to
+    int prefix_c0;            // K4p: first prefix length whose state is kept in shared memory
     int first_chunk;          // K3b: the scan starts here (behind the warm sample, whose lists split 0 inherits)
     int tile_offset;          // K3b: blockIdx.x + tile_offset = query tile (the tail launch covers the last tiles)
     int n_chunks;             // chunks to cover (ceil(n_scan / CHUNK))
@@ -93,5 +98,6 @@ int microbench_mma_i8(int variant, double *ops_per_s);
 int warm_window(Index *ix, const uint2 *qplanes, int64_t q, int k, int W, uint32_t *wlists, cudaStream_t st);
 void warm_free_index(Index *ix);
 int warm_copies();
+int sorted_by_prefix(Index *ix, cudaStream_t st);
 
 }  // namespace gm

@@ -176,10 +176,62 @@ static int warm_build_index(Index *ix, cudaStream_t st) {
 }
 
 void warm_free_index(Index *ix) {
+    dev_free(ix->prefix_p, 0); dev_free(ix->prefix_i, 0);
+    ix->prefix_p = nullptr; ix->prefix_i = nullptr;
     for (int c = 0; c < 4; c++) {
         dev_free(ix->sorted_p[c], 0); dev_free(ix->sorted_i[c], 0);
         ix->sorted_p[c] = nullptr; ix->sorted_i[c] = nullptr;
     }
+}
+
+// ---- K4p: the table sorted by the guides read from their FIRST base (knn.cu: knn_leven_prefix_kernel) ---------------
+__global__ void prefix_keys_kernel(const uint2 *__restrict__ planes, int64_t n, int L, uint64_t *__restrict__ keys, uint32_t *__restrict__ ids) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint2 p = planes[i];                                    // bit j = base j: reverse, so that base 0 is the most significant
+    keys[i] = from_planes(__brev(p.x) >> (32 - L), __brev(p.y) >> (32 - L));
+    ids[i] = (uint32_t)i;
+}
+__global__ void prefix_gather_kernel(const uint2 *__restrict__ planes, const uint32_t *__restrict__ ids, int64_t n, int64_t n_pad,
+                                     uint2 *__restrict__ out, uint32_t *__restrict__ ids_pad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    out[i] = i < n ? planes[ids[i]] : make_uint2(0u, 0u);
+    if (i >= n) ids_pad[i] = 0u;
+}
+
+int sorted_by_prefix(Index *ix, cudaStream_t st) {
+    if (ix->prefix_p) return GM_OK;
+    const int64_t n = ix->n_u, n_pad = ix->n_pad;
+    uint64_t *k_in = nullptr, *k_out = nullptr;
+    uint32_t *v_in = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cudaError_t e = dev_alloc((void **)&ix->prefix_i, (size_t)n_pad * 4, st);
+    if (e == cudaSuccess) e = dev_alloc((void **)&ix->prefix_p, (size_t)n_pad * 8, st);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, ix->prefix_i, (int)n, 0, 2 * ix->L, st);
+    if (e == cudaSuccess) e = dev_alloc((void **)&k_in, (size_t)n * 8, st);
+    if (e == cudaSuccess) e = dev_alloc((void **)&k_out, (size_t)n * 8, st);
+    if (e == cudaSuccess) e = dev_alloc((void **)&v_in, (size_t)n * 4, st);
+    if (e == cudaSuccess) e = dev_alloc(&tmp, tmp_bytes ? tmp_bytes : 1, st);
+    if (e == cudaSuccess) {
+        prefix_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ix->planes, n, ix->L, k_in, v_in);
+        count_launch();
+        e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, ix->prefix_i, (int)n, 0, 2 * ix->L, st);
+        count_launch(2 + (2 * ix->L + 7) / 8);
+    }
+    if (e == cudaSuccess) {
+        prefix_gather_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, st>>>(ix->planes, ix->prefix_i, n, n_pad, ix->prefix_p, ix->prefix_i);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    dev_free(k_in, st); dev_free(k_out, st); dev_free(v_in, st); dev_free(tmp, st);
+    if (e != cudaSuccess) {
+        dev_free(ix->prefix_p, st); dev_free(ix->prefix_i, st);
+        ix->prefix_p = nullptr; ix->prefix_i = nullptr;
+        return cuda_fail(e, "sorted_by_prefix", __FILE__, __LINE__);
+    }
+    return GM_OK;
 }
 
 // wlists ([q_pad][k], preset to KEY_EMPTY) <- k best of the copies x W guides around every query's rank in the sorted copies

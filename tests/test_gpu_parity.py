@@ -380,6 +380,37 @@ def test_knn_leven_warm_and_splits(capi):
             capi.knn_tune(8, 0, -1)
 
 
+@pytest.mark.parametrize("L,n,k,tune", [(20, 50000, 4, (8, 0, -1)), (8, 30000, 3, (8, 0, -1)), (27, 20000, 5, (8, 0, -1)),
+                                         (23, 40000, 2, (8, 5, 2048)), (20, 30000, 6, (4, 3, 0)), (9, 4096, 1, (8, 0, -1))])
+def test_knn_leven_prefix_sharing(capi_mod, L, n, k, tune):
+    """K4p (engine 1, the default for Levenshtein): the scan over the prefix-sorted copy of the table that resumes Myers'
+    recurrence from the state shared with the previous target; targets arrive out of index order, so ties at the k-th
+    distance exercise the full-key lists.  Against the oracle and against the plain kernel (engine 0)."""
+    rng = np.random.default_rng(60 + L + k)
+    if 4 ** L < 200000:
+        t = rng.permutation(4 ** L).astype(np.uint64)[:n]
+    else:
+        t, _ = O.unique_first_order(rand_guides(rng, n, L, n_base=n // 2))
+    mask = np.uint64((1 << (2 * L)) - 1)
+    sh = t[rng.integers(0, len(t), size=200)]
+    q = np.concatenate([rand_guides(rng, 400, L), (sh << np.uint64(2)) & mask, sh >> np.uint64(2), t[:100]])
+    capi_mod.knn_engine(1)
+    capi_mod.knn_tune(*tune)
+    try:
+        ix = capi_mod.Index(t, L, 1)
+        idx, dist = ix.knn(q, k)
+        oi, od = O.c_knn(t, q, L, 1, k)
+        assert np.array_equal(dist, od)
+        assert np.array_equal(idx, oi)
+        assert np.array_equal(ix.min_dist(q), od[:, 0])
+        ix.tune(engine=0)
+        ref = ix.knn(q, k)
+        assert np.array_equal(idx, ref[0]) and np.array_equal(dist, ref[1])
+        ix.close()
+    finally:
+        capi_mod.knn_tune(8, 0, -1)
+
+
 # ---- errors ---------------------------------------------------------------------------------------------------
 def test_argument_errors(capi):
     with pytest.raises(ValueError):
