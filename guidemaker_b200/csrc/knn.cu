@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(THREADS) knn_leven_prefix_kernel(const ScanArg
 
     int stage = 0;
     uint32_t parity = 0;
-    uint2 prev = make_uint2(0u, 0u);
+    uint64_t prev = 0;
     bool have_prev = false;
     for (int c = c0; c < c1; c++) {
         mbar_wait(&s_full[stage], parity);
@@ -330,13 +330,17 @@ __global__ void __launch_bounds__(THREADS) knn_leven_prefix_kernel(const ScanArg
         const int n_here = (int)min((int64_t)CHUNK, a.n_u - (int64_t)tbase);       // skip padding targets
 
         for (int g = 0; g < n_here; g++) {
-            const uint2 t = s_t[stage * CHUNK + g];         // CTA-uniform target
+            // CTA-uniform target, stored as its 2-bit code (base j = bits 2j, 2j+1): no per-target re-interleaving of planes
+            // (-6 %).  (Fetching the next target and its prefix length one iteration ahead was measured: +10 %, the values
+            // leave the uniform datapath.)
+            const uint2 t = s_t[stage * CHUNK + g];
             const uint32_t oidx = s_i[stage * CHUNK + g];
-            // common prefix with the previous target, in bases (bit j of the planes = base j of the text)
+            const uint64_t tcode = ((uint64_t)t.y << 32) | t.x;
+            // common prefix with the previous target, in bases
             int pl = 0;
-            if (have_prev) pl = min(__ffs((int)(((t.x ^ prev.x) | (t.y ^ prev.y)) | (1u << L))) - 1, lv_top);
+            if (have_prev) pl = min((__ffsll((long long)((tcode ^ prev) | (1ull << (2 * L)))) - 1) >> 1, lv_top);
             if (pl < lv0) pl = 0;
-            prev = t;
+            prev = tcode;
             have_prev = true;
             uint32_t Pv[R], Mv[R];
             if (pl == 0) {
@@ -347,7 +351,7 @@ __global__ void __launch_bounds__(THREADS) knn_leven_prefix_kernel(const ScanArg
 #pragma unroll
                 for (int r = 0; r < R; r++) { Pv[r] = s[(2 * r) * THREADS]; Mv[r] = s[(2 * r + 1) * THREADS]; }
             }
-            uint64_t code = (spread_bits(t.x) | (spread_bits(t.y) << 1)) >> (2 * pl);
+            uint64_t code = tcode >> (2 * pl);
 #pragma unroll 1
             for (int j = pl; j < L; j++) {
                 const uint32_t base = (uint32_t)code & 3u;   // the same in every lane: the switch is a uniform branch

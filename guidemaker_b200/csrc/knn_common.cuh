@@ -28,7 +28,8 @@ struct Index {
     // warm.cu: copies of the table sorted by guide with its positions rotated by c * L / copies, built lazily
     uint2 *sorted_p[4] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t *sorted_i[4] = {nullptr, nullptr, nullptr, nullptr};
-    // warm.cu: Levenshtein only -- the table sorted by the guides read from their first base (K4p), padded like `planes`
+    // warm.cu: Levenshtein only -- the table sorted by the guides read from their first base (K4p), as 2-bit codes
+    // (lo, hi word), padded like `planes`
     uint2 *prefix_p = nullptr;
     uint32_t *prefix_i = nullptr;
 };

@@ -196,7 +196,9 @@ __global__ void prefix_gather_kernel(const uint2 *__restrict__ planes, const uin
                                      uint2 *__restrict__ out, uint32_t *__restrict__ ids_pad) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
-    out[i] = i < n ? planes[ids[i]] : make_uint2(0u, 0u);
+    uint64_t code = 0;                                            // the kernel wants the 2-bit code (base j = bits 2j, 2j+1)
+    if (i < n) { const uint2 p = planes[ids[i]]; code = from_planes(p.x, p.y); }
+    out[i] = make_uint2((uint32_t)code, (uint32_t)(code >> 32));
     if (i >= n) ids_pad[i] = 0u;
 }
 
