@@ -438,7 +438,8 @@ def knn_tune(queries_per_thread: int = 0, splits: int = 0, warm_sample: int = -1
 
 
 def knn_engine(engine: int):
-    """0 = K3a XOR/POPC (INT pipes), 1 = K3b tcgen05 one-hot GEMM (tensor pipe)"""
+    """Hamming: 0 = K3a XOR/POPC (INT pipes), 1 = K3b tcgen05 int8 GEMM (tensor pipe); Levenshtein: 0 = plain scan,
+    1 = prefix-sorted table with shared DP states (K4p)"""
     _check(load_library().gm_knn_engine(int(engine)), "gm_knn_engine")
 
 

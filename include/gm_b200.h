@@ -206,11 +206,14 @@ int gm_prof_read(double *scan_kernel_ms, int64_t *scan_kernel_launches, double *
                  int64_t *all_kernel_launches);
 
 /* tuning knob for experiments and tests: queries per thread (4 or 8), target splits (0 = auto),
- * warm-start sample size (0 = off, -1 = default) */
+ * warm-start sample size (0 = off, -1 = default: for K3b on tables of >= 16384 guides the bound comes from the guides
+ * around every query's rank in three sorted copies of the table (warm.cu), no sample; > 0 = the first `warm_sample`
+ * guides of the table, scanned by a K3a / K4 launch) */
 int gm_knn_tune(int queries_per_thread, int splits, int warm_sample);
-/* Hamming pair-scan engine: 1 = K3b tcgen05 kind::i8 one-hot GEMM with the threshold test on the TMEM read-out
- * (default, ~3x faster), 0 = K3a XOR/POPC on the INT pipes.  Both are exact and return identical bits; the
- * Levenshtein metric always uses its own INT-pipe kernel.  DESIGN.md section 3. */
+/* Pair-scan engine.  Hamming: 1 = K3b tcgen05 kind::i8 GEMM over the 3-byte base code with the threshold test on the
+ * TMEM read-out (default, ~9x faster), 0 = K3a XOR/POPC on the INT pipes.  Levenshtein: 1 = K4p, Myers' recurrence over
+ * the prefix-sorted copy of the table with the DP states shared between consecutive guides (default, 1.55x), 0 = K4, the
+ * plain scan in index order.  Every engine is exact and returns identical bits.  DESIGN.md section 4. */
 int gm_knn_engine(int engine);
 /* The same knobs for ONE index handle, overriding the process-wide defaults above: engine -1 / queries_per_thread -1 /
  * splits -1 / warm_sample -2 = follow the default.  Two indices with different engines can live in one process. */
