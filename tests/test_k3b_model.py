@@ -17,7 +17,7 @@ def brute_topk(dist_row, k):
     return [(int(dist_row[i]), int(i)) for i in order]
 
 
-def run_protocol(dist, k, tile, rng, in_order=True, max_lag=6, warm=0):
+def run_protocol(dist, k, tile, rng, in_order=True, max_lag=6, warm=0, subset=None, inherit_subset=False):
     """dist: (Q, N) exact distances.  Returns per-query sorted lists of (distance, index)."""
     Q, N = dist.shape
     n_tiles = (N + tile - 1) // tile
@@ -30,6 +30,21 @@ def run_protocol(dist, k, tile, rng, in_order=True, max_lag=6, warm=0):
             if len(lists[q]) == k:
                 bound[q] = lists[q][-1]
                 bias[q] = lists[q][-1][0]
+    if subset is not None:
+        # neighbourhood warm start (warm.cu): per query an ARBITRARY subset of the table (any positions).  The kernel keeps
+        # only the subset's k-th distance w0, as an inclusive bound (w0 + 1, index 0) with empty lists.  inherit_subset
+        # models the tempting alternative -- inherit the subset's lists and flag strictly below w0 -- which loses ties.
+        for q in range(Q):
+            best = sorted((int(dist[q, i]), int(i)) for i in subset[q])[:k]
+            if len(best) < k:
+                continue
+            if inherit_subset:
+                lists[q] = list(best)
+                bound[q] = best[-1]
+                bias[q] = best[-1][0]
+            else:
+                bound[q] = (best[-1][0] + 1, -1)
+                bias[q] = best[-1][0] + 1
     first = warm // tile
     order = list(range(first, n_tiles))
     if not in_order:                                   # tiles may overtake each other by a few positions
@@ -59,7 +74,7 @@ def run_protocol(dist, k, tile, rng, in_order=True, max_lag=6, warm=0):
             a, b = tt * tile, min((tt + 1) * tile, N)
             for i in range(a, b):                      # exact re-check of every target of the chunk
                 key = (int(dist[q, i]), i)
-                if key < bound[q]:
+                if key < bound[q] and key not in lists[q]:
                     lists[q].append(key)
                     lists[q].sort()
                     del lists[q][k:]
@@ -70,7 +85,7 @@ def run_protocol(dist, k, tile, rng, in_order=True, max_lag=6, warm=0):
         a, b = tt * tile, min((tt + 1) * tile, N)
         for i in range(a, b):
             key = (int(dist[q, i]), i)
-            if key < bound[q]:
+            if key < bound[q] and key not in lists[q]:
                 lists[q].append(key)
                 lists[q].sort()
                 del lists[q][k:]
@@ -94,6 +109,36 @@ def test_filter_protocol_is_exact_for_any_staleness_and_service_order(seed):
     lists = run_protocol(dist, k, tile=32, rng=rng, in_order=True, warm=warm)
     for q in range(dist.shape[0]):
         assert lists[q] == brute_topk(dist[q], k), (seed, q)
+
+
+def _random_subsets(rng, Q, N, size):
+    return [rng.choice(N, size=size, replace=False) for _ in range(Q)]
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_bound_from_an_arbitrary_subset_is_exact_when_inclusive(seed):
+    """warm.cu + knn_tc.cu (warm_any_subset): the k-th distance over any k guides, taken as an inclusive bound with empty
+    lists, yields the exact (distance, index) top-k under the same staleness / service-order freedom"""
+    rng = np.random.default_rng(300 + seed)
+    dist = small_case(rng)
+    k = int(rng.choice([1, 2, 3, 5]))
+    subset = _random_subsets(rng, dist.shape[0], dist.shape[1], int(rng.choice([k, 8, 40])))
+    lists = run_protocol(dist, k, tile=32, rng=rng, in_order=True, subset=subset)
+    for q in range(dist.shape[0]):
+        assert lists[q] == brute_topk(dist[q], k), (seed, q)
+
+
+def test_inheriting_a_subsets_lists_with_a_strict_filter_loses_ties():
+    """why the kernel does NOT inherit the warm lists: a guide at exactly the subset's k-th distance but with a lower
+    index than the inherited entry is never flagged by the strict filter"""
+    bad = 0
+    for seed in range(30):
+        rng = np.random.default_rng(2000 + seed)
+        dist = small_case(rng)
+        subset = _random_subsets(rng, dist.shape[0], dist.shape[1], 40)
+        lists = run_protocol(dist, 3, tile=32, rng=rng, in_order=True, subset=subset, inherit_subset=True)
+        bad += sum(lists[q] != brute_topk(dist[q], 3) for q in range(dist.shape[0]))
+    assert bad > 0
 
 
 def test_out_of_order_tiles_can_lose_ties():
