@@ -331,8 +331,9 @@ __global__ void __launch_bounds__(THREADS) knn_leven_prefix_kernel(const ScanArg
 
         for (int g = 0; g < n_here; g++) {
             // CTA-uniform target, stored as its 2-bit code (base j = bits 2j, 2j+1): no per-target re-interleaving of planes
-            // (-6 %).  (Fetching the next target and its prefix length one iteration ahead was measured: +10 %, the values
-            // leave the uniform datapath.)
+            // (-6 %).  (Measured and dropped: fetching the next target and its prefix length one iteration ahead, +10 %;
+            // the prefix length precomputed into the spare high bits of the index word, +4 % -- in both the values leave
+            // the uniform datapath.)
             const uint2 t = s_t[stage * CHUNK + g];
             const uint32_t oidx = s_i[stage * CHUNK + g];
             const uint64_t tcode = ((uint64_t)t.y << 32) | t.x;
