@@ -47,6 +47,8 @@ _SIGS = {
     "gm_session_info": [_vp, _c_i64p] + [ctypes.POINTER(ctypes.c_int)] * 4,
     "gm_session_fetch_rows": [_vp, _vp, _vp, _vp, _vp, _vp],
     "gm_session_fetch_text": [_vp, _vp, _vp, ctypes.c_int, _vp],
+    "gm_session_pam_histogram": [_vp, _vp],
+    "gm_session_pam_categories": [_vp, _vp, _vp],
     "gm_session_seed_dedup": [_vp, ctypes.c_int, _vp],
     "gm_session_restriction": [_vp, _vp, _vp, ctypes.c_int, _vp],
     "gm_session_index": [_vp, ctypes.c_int, ctypes.POINTER(_vp), _vp, _vp, _c_i64p],
@@ -201,13 +203,29 @@ class Session:
                                                 ctypes.byref(self._h), ctypes.byref(n)), "gm_session_create")
         self.n_rows, self.L, self.P, self.five_prime = n.value, int(L), len(pam), bool(five_prime)
 
-    def fetch_rows(self):
-        """-> guide2bit u64[n], start u32[n] (record-relative), pamcode u16[n], rec i32[n], strand bool[n]"""
+    def fetch_rows(self, want_pamcode: bool = True):
+        """-> guide2bit u64[n], start u32[n] (record-relative), pamcode u16[n] (None if not wanted), rec i32[n], strand bool[n]"""
         n = self.n_rows
-        g = np.empty(n, np.uint64); s = np.empty(n, np.uint32); p = np.empty(n, np.uint16); r = np.empty(n, np.int32); f = np.empty(n, np.uint8)
+        g = np.empty(n, np.uint64); s = np.empty(n, np.uint32); r = np.empty(n, np.int32); f = np.empty(n, np.uint8)
+        p = np.empty(n, np.uint16) if want_pamcode else None
         if n:
-            _check(load_library().gm_session_fetch_rows(self._h, _p(g), _p(s), _p(p), _p(r), _p(f)), "gm_session_fetch_rows")
+            _check(load_library().gm_session_fetch_rows(self._h, _p(g), _p(s), _p(p) if want_pamcode else None, _p(r), _p(f)),
+                   "gm_session_fetch_rows")
         return g, s, p, r, f.view(np.bool_)
+
+    def pam_histogram(self) -> np.ndarray:
+        """how often each of the 65536 possible packed PAM codes occurs among the rows"""
+        h = np.zeros(1 << 16, np.uint32)
+        _check(load_library().gm_session_pam_histogram(self._h, _p(h)), "gm_session_pam_histogram")
+        return h
+
+    def pam_categories(self, lut: np.ndarray) -> np.ndarray:
+        """int8 category code of every row: lut[pamcode[row]] evaluated on the device"""
+        lut = np.ascontiguousarray(lut, np.int8)
+        assert lut.shape == (1 << 16,)
+        out = np.empty(self.n_rows, np.int8)
+        _check(load_library().gm_session_pam_categories(self._h, _p(lut), _p(out) if self.n_rows else None), "gm_session_pam_categories")
+        return out
 
     def fetch_text(self, width: int = 30):
         """-> target ASCII (n, L), context ASCII (n, width), edge bool[n] (context window leaves its record: row is '?')"""

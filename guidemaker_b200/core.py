@@ -186,12 +186,17 @@ class PamTarget:
         n = sess.n_rows
         if n == 0:
             return pd.concat([])                     # zero hits -> ValueError (core.py:286-287)
-        guides, start, pamcode, rec, strand = sess.fetch_rows()
+        # exact_pam: the device counts the distinct packed PAM codes and, given the code -> category table, returns one int8
+        # category per row; the uint16 code column only crosses PCIe when there are too many distinct PAMs for int8
+        exact_pam = self._pam_categorical_dev(sess, P)
+        guides, start, pamcode, rec, strand = sess.fetch_rows(want_pamcode=exact_pam is None)
+        if exact_pam is None:
+            exact_pam = self._pam_categorical(pamcode, P)
         target_mat, ctx, edge = sess.fetch_text(30)
         seq30 = self._target_seq30(ctx, edge, seqs, rec, start, strand, five, P, L)
         df = pd.DataFrame({
             "target": _str_series(target_mat),
-            "exact_pam": self._pam_categorical(pamcode, P),
+            "exact_pam": exact_pam,
             "start": start,
             "stop": start + np.uint32(L),
             "strand": strand,
@@ -220,9 +225,36 @@ class PamTarget:
         if len(set(ids)) != len(ids):
             return pd.Categorical(np.asarray(ids, dtype=object)[rec])
         order = sorted(range(len(ids)), key=lambda i: ids[i])
-        inv = np.empty(len(ids), dtype=np.int64)
+        inv = np.empty(len(ids), dtype=np.int8 if len(ids) < 128 else np.int32)
         inv[order] = np.arange(len(ids))
-        return pd.Categorical.from_codes(inv[rec], categories=pd.Index([ids[i] for i in order]))
+        # the rows come grouped by record in ascending record order (the session's row order), so the code column is a
+        # run-length expansion: record boundaries by binary search instead of a gather over all rows
+        cuts = np.searchsorted(rec, np.arange(len(ids) + 1))
+        runs = np.flatnonzero(cuts[1:] > cuts[:-1])   # records that have rows; each run must start and end with its record
+        if cuts[0] == 0 and cuts[-1] == len(rec) and np.array_equal(rec[cuts[runs]], runs) and np.array_equal(rec[cuts[runs + 1] - 1], runs):
+            codes = np.repeat(inv, np.diff(cuts))
+        else:
+            codes = inv[rec]                          # not grouped (a caller-made `rec`): plain gather
+        return pd.Categorical.from_codes(codes, categories=pd.Index([ids[i] for i in order]), validate=False)
+
+    @staticmethod
+    def _pam_categories(present: np.ndarray, P: int):
+        """(category strings in sorted order, rank of each present code in that order)"""
+        cats = [b.decode() for b in decode_matrix(present.astype(np.uint64), P).view("S%d" % P).reshape(-1)] if P else [""] * len(present)
+        order = np.argsort(np.array(cats, dtype=object), kind="stable")
+        return [cats[i] for i in order], order
+
+    @classmethod
+    def _pam_categorical_dev(cls, sess, P: int):
+        """exact_pam from the session: histogram of the packed codes and the per-row category on the device (None when
+        the genome shows 128 or more distinct PAMs: the caller then builds the column from the code column)"""
+        present = np.flatnonzero(sess.pam_histogram())
+        if len(present) >= 128:
+            return None
+        cats, order = cls._pam_categories(present, P)
+        lut = np.zeros(1 << 16, dtype=np.int8)
+        lut[present[order]] = np.arange(len(present), dtype=np.int8)
+        return pd.Categorical.from_codes(sess.pam_categories(lut), categories=pd.Index(cats, dtype="str"), validate=False)
 
     @staticmethod
     def _pam_categorical(pamcode: np.ndarray, P: int) -> pd.Categorical:

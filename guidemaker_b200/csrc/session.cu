@@ -68,6 +68,23 @@ static Scan *as_session(void *h) {
 
 using namespace gm;
 
+// ---- exact_pam as a categorical on the device (core.py:167,195,222,248 build it from n Python strings) -----------------
+// histogram of the packed PAM codes: lanes holding the same code elect one to add their count (a genome has a handful of
+// distinct PAMs, so plain atomics would all hit the same few words)
+__global__ void pam_hist_kernel(const uint16_t *__restrict__ pamcode, int64_t n, unsigned int *__restrict__ hist) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = i < n;
+    const unsigned active = __ballot_sync(0xFFFFFFFFu, in);
+    if (!in) return;
+    const unsigned code = pamcode[i];
+    const unsigned peers = __match_any_sync(active, code);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[code], (unsigned)__popc(peers));
+}
+__global__ void pam_lut_kernel(const uint16_t *__restrict__ pamcode, int64_t n, const int8_t *__restrict__ lut, int8_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = lut[pamcode[i]];
+}
+
 extern "C" int gm_session_info(void *session, int64_t *n_rows, int *n_rec, int *L, int *P, int *five_prime) {
     Scan *s = as_session(session);
     GM_ARG(s, "gm_session_info: not a session handle");
@@ -394,5 +411,49 @@ extern "C" int gm_session_fetch_neighbors(void *session, uint64_t *codes, int32_
     dev_free(s->nb_codes, 0); dev_free(s->nb_idx, 0); dev_free(s->nb_dist, 0);
     s->nb_codes = nullptr; s->nb_idx = nullptr; s->nb_dist = nullptr; s->nb_rows = 0;
     trace("session: fetch neighbours", t0);
+    return GM_OK;
+}
+
+extern "C" int gm_session_pam_histogram(void *session, uint32_t *hist65536) {
+    Scan *s = (Scan *)session;
+    GM_ARG(s && s->session && hist65536, "gm_session_pam_histogram: bad argument");
+    const int64_t nt = s->n_fwd + s->n_rev;
+    unsigned int *d = nullptr;
+    GM_CUDA(dev_alloc((void **)&d, 65536 * sizeof(unsigned int), 0));
+    cudaError_t e = cudaMemsetAsync(d, 0, 65536 * sizeof(unsigned int), 0);
+    if (e == cudaSuccess && nt > 0) {
+        pam_hist_kernel<<<(unsigned)((nt + 255) / 256), 256>>>(s->pamcode, nt, d);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hist65536, d, 65536 * sizeof(unsigned int), cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    dev_free(d, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "gm_session_pam_histogram", __FILE__, __LINE__);
+    return GM_OK;
+}
+
+extern "C" int gm_session_pam_categories(void *session, const int8_t *lut65536, int8_t *codes) {
+    Scan *s = (Scan *)session;
+    GM_ARG(s && s->session && lut65536, "gm_session_pam_categories: bad argument");
+    const int64_t nt = s->n_fwd + s->n_rev;
+    if (nt == 0) return GM_OK;
+    GM_ARG(codes, "gm_session_pam_categories: NULL output");
+    int8_t *d_lut = nullptr, *d_out = nullptr;
+    cudaError_t e = dev_alloc((void **)&d_lut, 65536, 0);
+    if (e == cudaSuccess) e = dev_alloc((void **)&d_out, (size_t)nt, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_lut, lut65536, 65536, cudaMemcpyHostToDevice, 0);
+    if (e == cudaSuccess) {
+        pam_lut_kernel<<<(unsigned)((nt + 255) / 256), 256>>>(s->pamcode, nt, d_lut, d_out);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) {
+        prefault(codes, (size_t)nt);
+        e = cudaMemcpyAsync(codes, d_out, (size_t)nt, cudaMemcpyDeviceToHost, 0);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    dev_free(d_lut, 0); dev_free(d_out, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "gm_session_pam_categories", __FILE__, __LINE__);
     return GM_OK;
 }

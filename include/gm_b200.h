@@ -110,6 +110,9 @@ int gm_scan_device_ptrs(void *scan, const uint64_t **d_guide2bit, const uint32_t
  * hits ascending, then reverse hits ascending; core.py:254-284) with record-relative coordinates, and (b) keeps genome and
  * rows resident in HBM so that the later stages run off the handle without re-uploading anything:
  *   gm_session_fetch_rows   the numeric columns of find_targets' frame (any pointer may be NULL)
+ *   gm_session_pam_histogram / gm_session_pam_categories   `exact_pam` as a categorical without n strings: the counts of the
+ *                           65536 possible packed PAM codes, then -- with a caller-made code -> category table -- one int8
+ *                           category code per row (core.py:167,195,222,248 build the column from Python strings)
  *   gm_session_fetch_text   `target` as ASCII (n_rows x L) and the 30-nt context `target_seq30` (n_rows x width) gathered
  *                           from the resident genome (core.py:156,184,210-211,237); edge[i] = 1 where the window leaves
  *                           the record (filled with '?': the caller applies Python's slice semantics to those rows)
@@ -125,6 +128,8 @@ int gm_session_create(const uint8_t *seq_ascii, int64_t n, const int64_t *rec_st
 int gm_session_info(void *session, int64_t *n_rows, int *n_rec, int *L, int *P, int *five_prime);
 int gm_session_fetch_rows(void *session, uint64_t *guide2bit, uint32_t *start, uint16_t *pamcode, int32_t *rec, uint8_t *strand);
 int gm_session_fetch_text(void *session, uint8_t *target_ascii, uint8_t *context, int width, uint8_t *edge);
+int gm_session_pam_histogram(void *session, uint32_t *hist65536);
+int gm_session_pam_categories(void *session, const int8_t *lut65536, int8_t *codes);
 int gm_session_seed_dedup(void *session, int lsr, uint8_t *is_dup);
 int gm_session_restriction(void *session, const uint8_t *motif_sets, const int32_t *motif_len, int n_motifs, uint8_t *has_site);
 int gm_session_index(void *session, int metric, void **index, uint64_t *uniq2bit, int32_t *row2uniq, int64_t *n_u);

@@ -112,8 +112,14 @@ class _OracleSession:
         self.start = (self.gstart - self.rec_start[self.rec]).astype(np.uint32)
         self.n_rows = len(self.g)
 
-    def fetch_rows(self):
-        return self.g, self.start, self.p, self.rec, self.strand
+    def fetch_rows(self, want_pamcode=True):
+        return self.g, self.start, (self.p if want_pamcode else None), self.rec, self.strand
+
+    def pam_histogram(self):
+        return np.bincount(self.p, minlength=1 << 16).astype(np.uint32)
+
+    def pam_categories(self, lut):
+        return np.asarray(lut, np.int8)[self.p]
 
     def fetch_text(self, width=30):
         from guidemaker_b200._encode import decode_matrix

@@ -68,6 +68,13 @@ def test_session_rows_and_text_vs_oracle(capi, name):
     assert s.n_rows == o.n_rows and s.n_rows > 100
     for a, b, what in zip(s.fetch_rows(), o.fetch_rows(), ("guides", "start", "pamcode", "rec", "strand")):
         assert np.array_equal(a, b), what
+    # exact_pam on the device: histogram of the packed codes, per-row category through a caller-made table
+    g, st, p, r, f = s.fetch_rows(want_pamcode=False)
+    assert p is None and np.array_equal(g, o.g) and np.array_equal(r, o.rec)
+    hist = s.pam_histogram()
+    assert hist.dtype == np.uint32 and np.array_equal(hist, np.bincount(o.p, minlength=1 << 16))
+    lut = rng.integers(-128, 128, size=1 << 16).astype(np.int8)
+    assert np.array_equal(s.pam_categories(lut), lut[o.p])
     t, c, e = s.fetch_text(30)
     ot, oc, oe = o.fetch_text(30)
     assert np.array_equal(t, ot) and np.array_equal(e, oe) and (e.any() or name not in ("ngg3p20", "ngg5p20"))

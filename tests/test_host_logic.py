@@ -245,3 +245,18 @@ def test_api_under_two_ranks_gloo(tmp_path):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and "RANK_OK %d" % r in o, o
+
+
+def test_seqid_categorical_run_lengths_and_fallback():
+    """find_targets builds `seqid` by run-length expansion when the rows are grouped by record (the session's order) and by
+    a plain gather otherwise; categories are lexicographic either way, and records without rows stay categories"""
+    import pandas as pd
+    from guidemaker_b200.core import PamTarget
+    ids = ["chrB", "chrA", "empty", "chrC"]
+    grouped = np.array([0, 0, 0, 1, 3, 3], np.int32)
+    shuffled = np.array([3, 0, 1, 0, 3, 0], np.int32)
+    for rec in (grouped, shuffled, np.zeros(0, np.int32)):
+        c = PamTarget._seqid_categorical(ids, rec)
+        want = pd.Categorical([ids[i] for i in rec], categories=sorted(ids))
+        assert list(c.categories) == sorted(ids)
+        assert list(c) == list(want) and np.array_equal(c.codes, want.codes)
