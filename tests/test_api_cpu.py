@@ -42,3 +42,28 @@ def test_errors(oracle_engine, config_yaml):
 
 def test_unsorted_contigs(oracle_engine, config_yaml):
     C.case_unsorted_contigs(config_yaml)
+
+
+def test_exact_pam_with_many_distinct_pams(oracle_engine):
+    """256 distinct PAMs ('NNNN') do not fit the int8 categories the session returns: find_targets falls back to the code
+    column; either way exact_pam equals a Categorical of the literal PAM strings (sorted categories)"""
+    import numpy as np
+    import pandas as pd
+    from guidemaker_b200 import PamTarget
+
+    class Rec:
+        def __init__(self, i, s):
+            self.id, self.seq = i, s
+
+    rng = np.random.default_rng(17)
+    recs = [Rec("r%d" % i, "".join(rng.choice(list("ACGT"), size=4000))) for i in range(2)]
+    for pam, n_cat in (("NNNN", 256), ("NNG", 16)):
+        df = PamTarget(pam, "3prime", "hamming").find_targets(recs, 12)
+        assert len(df["exact_pam"].cat.categories) == n_cat
+        assert list(df["exact_pam"].cat.categories) == sorted(df["exact_pam"].cat.categories)
+        # forward rows: the PAM is the text right behind the target
+        fwd = df[df["strand"] & (df["seqid"] == "r0")]
+        lit = [recs[0].seq[int(e): int(e) + len(pam)] for e in fwd["stop"]]
+        assert fwd["exact_pam"].astype(str).tolist() == lit
+        want = pd.Categorical(df["exact_pam"].astype(str))
+        assert np.array_equal(df["exact_pam"].cat.codes, want.codes)
